@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the CPD detection hot path on B200 (contract: see task brief).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, libcpd_b200.so)
+  python bench.py --impl reference ...                     # CPU arm: the oracle port of the
+                                                           # reference path on the host cores
+One "step" = one pass of the hot path over one batch of synthetic Waymo-shaped sweeps.
+`value` has the point clouds already resident in HBM; `e2e` goes through the public API with
+HOST (pinned) buffers, H2D and D2H inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames_per_sec"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="backbone_fwd", choices=["backbone_fwd"])
+    ap.add_argument("--batch", type=int, default=4, help="frames per step per GPU (CPD trains with 4)")
+    ap.add_argument("--points", type=int, default=160000, help="points per frame")
+    ap.add_argument("--pool", type=int, default=2, help="distinct batches cycled through")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"CPD VoxelBackBone8x fwd (voxelize+MeanVFE+12 sparse convs+BEV dense), {a.points // 1000}k pts/frame, "
+            f"bs={a.batch}/GPU [BASELINE configs[1]]")
+
+
+def make_frames(rank, count, points):
+    from cpd_b200.synth import synth_scan
+    return [synth_scan(points, 1000 * rank + i) for i in range(count)]
+
+
+def make_net(device):
+    import torch
+    from cpd_b200 import backbone
+    torch.manual_seed(1234)
+    net = backbone.VoxelBackBone8x(dict(NUM_FILTERS=[16, 32, 64, 128], OUT_FEATURES=128), 5, [1504, 1504, 40])
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.uniform_(-0.1, 0.1)
+            m.running_var.uniform_(0.8, 1.2)
+    return net.to(device).eval()
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.rows, self.gpu, self.proc = [], gpu_index, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([t.strip() for t in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from cpd_b200 import _lib, backbone, ops, voxel
+    from cpd_b200.synth import PC_RANGE, VOXEL_SIZE
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+    net = make_net(dev)
+    to_bev = backbone.HeightCompression()
+    frames = make_frames(rank, a.batch * a.pool, a.points)
+    host = [torch.from_numpy(f).pin_memory() for f in frames]
+    resident = [h.to(dev) for h in host]
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def step(points_list):
+        bd = voxel.voxelize_batch(points_list, PC_RANGE, VOXEL_SIZE)
+        bd["batch_size"] = len(points_list)
+        out = to_bev(net(bd))
+        return out["spatial_features"], out["encoded_spconv_tensor"]
+
+    def batch_of(i, src):
+        k = (i % a.pool) * a.batch
+        return src[k:k + a.batch]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(a.warmup):
+            step(batch_of(i, resident))
+        barrier()
+        # ---- timed region: K steps, inputs resident in HBM, L2 flushed between steps ----
+        sampler = ClockSampler(local)
+        sampler.start()
+        ops.PROFILE = []
+        l0 = _lib.launch_count()
+        evs = []
+        barrier()
+        for i in range(a.steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            bev, enc = step(batch_of(i, resident))
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        launches = _lib.launch_count() - l0
+        prof, ops.PROFILE = ops.PROFILE, None
+        clocks = sampler.stop()
+        total_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+        # ---- end-to-end: host (pinned) points in, result checksum out, every step ----
+        evs2 = []
+        h2d = d2h = 0
+        barrier()
+        for i in range(a.steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pl = [h.to(dev, non_blocking=True) for h in batch_of(i, host)]
+            bev, enc = step(pl)
+            res = torch.stack([bev.sum(), enc.features.abs().max()]).cpu()
+            e1.record()
+            evs2.append((e0, e1))
+            h2d = sum(h.numel() * 4 for h in batch_of(i, host))
+            d2h = res.numel() * 4 + 4 * (len(pl) + 1) + 4 * 4      # result + voxel counts + 4 strided n_out reads
+        barrier()
+        e2e_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs2)
+
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+    frames_total = a.batch * a.steps * world
+
+    # ---- roofline of the dominant kernel family (gather-GEMM), per layer shape ----
+    hbm, bf16, src = peaks()
+    groups, pcache = {}, {}
+    for e0, e1, m in prof:
+        key = (m["cin"], m["cout"], m["K"])
+        nid = id(m["nbr"])
+        if nid not in pcache:
+            pcache[nid] = int((m["nbr"] >= 0).sum().item())
+        P = pcache[nid]
+        g = groups.setdefault(key, dict(ms=0.0, n=0, bytes=0.0, flops=0.0))
+        g["ms"] += e0.elapsed_time(e1); g["n"] += 1
+        g["bytes"] += 4.0 * (m["m_in"] * m["cin"] + m["m_out"] * m["cout"]) + 8.0 * P + 4.0 * m["K"] * m["cin"] * m["cout"]
+        g["flops"] += 2.0 * P * m["cin"] * m["cout"]
+    gg_ms = sum(g["ms"] for g in groups.values())
+    top_key, top = max(groups.items(), key=lambda kv: kv[1]["ms"])
+    ai = top["flops"] / max(top["bytes"], 1.0)
+    tf32_peak = bf16 / 2.0
+    if ai * hbm / 1e3 < tf32_peak:            # below the ridge: HBM bound
+        roof = dict(bound="hbm", achieved=top["bytes"] / top["ms"] / 1e6, peak=hbm, unit="GB/s")
+    else:
+        roof = dict(bound="tensor", achieved=top["flops"] / top["ms"] / 1e9, peak=tf32_peak, unit="TFLOP/s")
+    roof.update(frac=roof["achieved"] / roof["peak"], traffic=None, peak_source=f"{src} ({'HBM copy' if roof['bound'] == 'hbm' else 'bf16/2 = TF32 dense'})",
+                kernel=f"gather_gemm {top_key[0]}->{top_key[1]} K={top_key[2]}", launches=top["n"],
+                avg_launch_us=1e3 * top["ms"] / top["n"], share_of_step=top["ms"] / total_ms,
+                gather_gemm_share_of_step=gg_ms / total_ms,
+                algorithmic_bytes_per_launch=top["bytes"] / top["n"], flops_per_launch=top["flops"] / top["n"])
+
+    line = {
+        "metric": METRIC, "value": frames_total / (total_ms / 1e3), "unit": "frames/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "frames_per_step_per_gpu": a.batch, "points_per_frame": a.points,
+                   "voxel_size": [0.1, 0.1, 0.15], "grid": [1504, 1504, 40], "parallelism": f"dp{world}",
+                   "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write)",
+                   "active_voxels_last_batch": int(enc.indices.shape[0])},
+        "e2e": {"value": frames_total / (e2e_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+    }
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(a, frames[:1], net)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(a, frames, net=None):
+    """Oracle port of the same path (voxelize -> MeanVFE -> sparse convs -> dense) on the host cores."""
+    from cpd_b200.synth import PC_RANGE, VOXEL_SIZE
+    from oracle import oracle as O
+    from oracle import pipeline
+    if net is None:
+        import torch
+        net = make_net(torch.device("cpu"))
+    cores = os.cpu_count() or 1
+    O.set_threads(cores)
+    pipeline.backbone_forward(net, [frames[0][:20000]], PC_RANGE, VOXEL_SIZE)      # warm caches / page in
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        feats, coords, shape, _ = pipeline.backbone_forward(net, [frames[n % len(frames)]], PC_RANGE, VOXEL_SIZE)
+        pipeline.bev_dense(feats, coords, 1, shape)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > 10.0 or n >= 8:
+            break
+    return {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{n} frame(s) of the same workload ({a.points} pts), oracle/cpd_oracle.c with OpenMP on {cores} threads"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames = make_frames(0, 1, a.points)
+    steps, vals = max(1, min(a.steps, 3)), []
+    base = None
+    for _ in range(max(1, min(a.warmup, 1)) + steps):
+        base = cpu_baseline(a, frames)
+        vals.append(base["value"])
+    v = float(np.mean(vals[-steps:]))
+    base["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * a.batch / v, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "frames_per_step_per_gpu": a.batch, "points_per_frame": a.points,
+                   "note": "spconv-cu111 is not installable here; this arm is the CPU oracle port of the same path"},
+        "cpu_baseline": base,
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

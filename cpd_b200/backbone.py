@@ -1,0 +1,227 @@
+"""Sparse 3-D backbones of CPD rebuilt on cpd_b200.sparse.
+
+Host-side mirror of cpd/models/backbones_3d/spconv_backbone.py: ``VoxelBackBone8x``
+(:138-395) and ``VoxelResBackBone8x`` (:398-600) with the same constructor signature,
+config keys (NUM_FILTERS, OUT_FEATURES, RETURN_NUM_FEATURES_AS_DICT, MM, last_pad), module
+names (=> identical state_dict keys, so CPD checkpoints load), indice_keys and batch_dict
+contract.  The reference classes themselves also run unchanged on the
+``cpd_b200.compat`` spconv shim; these mirrors exist so that the hot path can be built and
+benchmarked without the reference tree, and so that the residual blocks can use the fused
+conv+BN+residual+ReLU epilogue in eval mode.
+"""
+from functools import partial
+
+import torch
+import torch.nn as nn
+
+from . import sparse as sp
+from .sparse import fold_bn
+
+
+class _Cfg(dict):
+    """dict with attribute access (stand-in for the reference's EasyDict model_cfg)."""
+    __getattr__ = dict.get
+
+
+def _cfg(c):
+    return c if hasattr(c, "get") and not isinstance(c, dict) else _Cfg(c or {})
+
+
+def conv_bn_relu(cin, cout, ksize, norm_fn, indice_key=None, stride=1, padding=0, conv_type="subm"):
+    """post_act_block (spconv_backbone.py:13-35): conv(bias=False) + BN + ReLU."""
+    if conv_type == "subm":
+        conv = sp.SubMConv3d(cin, cout, ksize, bias=False, indice_key=indice_key)
+    elif conv_type == "spconv":
+        conv = sp.SparseConv3d(cin, cout, ksize, stride=stride, padding=padding, bias=False, indice_key=indice_key)
+    elif conv_type == "inverseconv":
+        conv = sp.SparseInverseConv3d(cin, cout, ksize, indice_key=indice_key, bias=False)
+    else:
+        raise NotImplementedError(conv_type)
+    return sp.SparseSequential(conv, norm_fn(cout), nn.ReLU())
+
+
+class SparseBasicBlock(sp.SparseModule):
+    """Residual block of spconv_backbone.py:100-136: two SubM 3x3x3 convs (bias=True), BN after
+    each, ReLU after the first and after the residual add."""
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, norm_fn=None, downsample=None, indice_key=None):
+        super().__init__()
+        assert norm_fn is not None
+        self.conv1 = sp.SubMConv3d(inplanes, planes, 3, stride=stride, padding=1, bias=True, indice_key=indice_key)
+        self.bn1 = norm_fn(planes)
+        self.relu = nn.ReLU()
+        self.conv2 = sp.SubMConv3d(planes, planes, 3, stride=stride, padding=1, bias=True, indice_key=indice_key)
+        self.bn2 = norm_fn(planes)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        if not self.training and not torch.is_grad_enabled() and self.downsample is None:
+            s1, h1 = fold_bn(self.bn1)
+            s2, h2 = fold_bn(self.bn2)
+            out = self.conv1.forward_fused(x, s1, h1, relu=True)
+            return self.conv2.forward_fused(out, s2, h2, relu=True, residual=x.features)
+        identity = x
+        out = self.conv1(x)
+        out = out.replace_feature(self.relu(self.bn1(out.features)))
+        out = self.conv2(out)
+        out = out.replace_feature(self.bn2(out.features))
+        if self.downsample is not None:
+            identity = self.downsample(x)
+        return out.replace_feature(self.relu(out.features + identity.features))
+
+
+class _Backbone8xBase(nn.Module):
+    RES = False
+
+    def __init__(self, model_cfg, input_channels, grid_size, num_frames=1, **kwargs):
+        super().__init__()
+        cfg = _cfg(model_cfg)
+        self.model_cfg = cfg
+        self.num_frames = num_frames
+        self.return_num_features_as_dict = cfg.get("RETURN_NUM_FEATURES_AS_DICT", False)
+        self.out_features = cfg.get("OUT_FEATURES", 128)
+        nf = cfg.get("NUM_FILTERS", [16, 32, 64, 128])
+        norm_fn = partial(nn.BatchNorm1d, eps=1e-3, momentum=0.01)
+        gs = [int(g) for g in grid_size]
+        self.sparse_shape = [gs[2] + 1, gs[1], gs[0]]          # grid_size[::-1] + [1, 0, 0]
+        self._build_tower("", input_channels, nf, norm_fn, full=True)
+        last_pad = cfg.get("last_pad", 0)
+        self.conv_out = sp.SparseSequential(
+            sp.SparseConv3d(nf[3], self.out_features, (3, 1, 1), stride=(2, 1, 1), padding=last_pad, bias=False,
+                            indice_key="spconv_down2"),
+            norm_fn(self.out_features), nn.ReLU())
+        if cfg.get("MM", False):
+            self._build_tower("_2", input_channels, nf, norm_fn, full=not self.RES)
+        self.num_point_features = self.out_features
+        if self.return_num_features_as_dict:
+            self.num_point_features = {"x_conv1": nf[0], "x_conv2": nf[1], "x_conv3": nf[2], "x_conv4": nf[3]}
+
+    def _stage_blocks(self, c, norm_fn, key, n):
+        if self.RES:
+            return [SparseBasicBlock(c, c, norm_fn=norm_fn, indice_key=key) for _ in range(n)]
+        return [conv_bn_relu(c, c, 3, norm_fn, indice_key=key, padding=1) for _ in range(n)]
+
+    def _build_tower(self, sfx, cin, nf, norm_fn, full):
+        k = (lambda name: name + sfx)
+        sub = "res" if self.RES else "subm"
+        # Res tower indexes its stage-1 convs 'subm1' (input) and 'res1' (blocks); plain tower shares 'subm1'
+        setattr(self, "conv_input" + sfx, sp.SparseSequential(
+            sp.SubMConv3d(cin, nf[0], 3, padding=1, bias=False, indice_key=k("subm1")), norm_fn(nf[0]), nn.ReLU()))
+        n1 = 2 if self.RES else 1
+        setattr(self, "conv1" + sfx, sp.SparseSequential(*self._stage_blocks(nf[0], norm_fn, k(sub + "1"), n1)))
+        pads = {2: 1, 3: 1, 4: (0, 1, 1)}
+        for s in (2, 3, 4):
+            n = 2 if full else 1
+            down = conv_bn_relu(nf[s - 2], nf[s - 1], 3, norm_fn, stride=2, padding=pads[s], indice_key=k(f"spconv{s}"),
+                                conv_type="spconv")
+            setattr(self, f"conv{s}" + sfx, sp.SparseSequential(down, *self._stage_blocks(nf[s - 1], norm_fn, k(f"{sub}{s}"), n)))
+
+    def _run_tower(self, sfx, feats, coords, batch_size, with_out):
+        x = sp.SparseConvTensor(feats, coords.int() if coords.dtype != torch.int32 else coords, self.sparse_shape, batch_size)
+        x = getattr(self, "conv_input" + sfx)(x)
+        c1 = getattr(self, "conv1" + sfx)(x)
+        c2 = getattr(self, "conv2" + sfx)(c1)
+        c3 = getattr(self, "conv3" + sfx)(c2)
+        c4 = getattr(self, "conv4" + sfx)(c3)
+        out = self.conv_out(c4) if with_out else None
+        return out, {"x_conv1": c1, "x_conv2": c2, "x_conv3": c3, "x_conv4": c4}
+
+    _STRIDES = {"x_conv1": 1, "x_conv2": 2, "x_conv3": 4, "x_conv4": 8}
+
+
+class VoxelResBackBone8x(_Backbone8xBase):
+    """spconv_backbone.py:398-600: residual tower; in training with MM a second tower
+    (``*_2`` modules, one block per stage from stage 2 on, no conv_out) runs on
+    ``voxel_features1`` / ``voxel_coords1`` (:560-598)."""
+    RES = True
+
+    def forward(self, batch_dict):
+        bs = batch_dict["batch_size"]
+        out, ms = self._run_tower("", batch_dict["voxel_features"], batch_dict["voxel_coords"], bs, True)
+        batch_dict.update({"encoded_spconv_tensor": out, "encoded_spconv_tensor_stride": 8,
+                           "multi_scale_3d_features": ms, "multi_scale_3d_strides": dict(self._STRIDES)})
+        if self.training and self.model_cfg.get("MM", False):
+            _, ms2 = self._run_tower("_2", batch_dict["voxel_features1"], batch_dict["voxel_coords1"], bs, False)
+            batch_dict.update({"encoded_spconv_tensor_stride_mm": 8, "multi_scale_3d_features_mm": ms2,
+                               "multi_scale_3d_strides": dict(self._STRIDES)})
+        return batch_dict
+
+
+class VoxelBackBone8x(_Backbone8xBase):
+    """spconv_backbone.py:138-395: plain tower.  Training loops the stages separately
+    (:285-331); eval concatenates the stages along X into one [D, H, 4*W] tensor and splits
+    the results with ``decompose_tensor`` whose strict ``<`` bounds are kept (:241-260,332-393)."""
+    RES = False
+
+    def decompose_tensor(self, tensor, i, batch_size):
+        w4 = tensor.spatial_shape[2] // 4
+        lo, hi = i * w4, (i + 1) * w4
+        x = tensor.indices[:, 3]
+        mask = (lo < x) & (x < hi)
+        coords = tensor.indices[mask].clone()
+        coords[:, 3] -= lo
+        return sp.SparseConvTensor(tensor.features[mask], coords.int().contiguous(),
+                                   [tensor.spatial_shape[0], tensor.spatial_shape[1], w4], batch_size)
+
+    def forward(self, batch_dict):
+        stages = batch_dict["transform_param"].shape[1] if "transform_param" in batch_dict else 1
+        bs = batch_dict["batch_size"]
+        sid = lambda i: "" if i == 0 else str(i)
+        if self.training:
+            for i in range(stages):
+                out, ms = self._run_tower("", batch_dict["voxel_features" + sid(i)], batch_dict["voxel_coords" + sid(i)], bs, True)
+                batch_dict.update({"encoded_spconv_tensor" + sid(i): out, "encoded_spconv_tensor_stride" + sid(i): 8,
+                                   "multi_scale_3d_features" + sid(i): ms,
+                                   "multi_scale_3d_strides" + sid(i): dict(self._STRIDES)})
+            return batch_dict
+        feats, coords = [], []
+        for i in range(stages):
+            feats.append(batch_dict["voxel_features" + sid(i)])
+            c = batch_dict["voxel_coords" + sid(i)].clone()
+            c[:, 3] += i * self.sparse_shape[2]
+            coords.append(c)
+        wide = [self.sparse_shape[0], self.sparse_shape[1], self.sparse_shape[2] * 4]
+        keep = self.sparse_shape
+        self.sparse_shape = wide
+        try:
+            out, ms = self._run_tower("", torch.cat(feats, 0), torch.cat(coords, 0), bs, True)
+        finally:
+            self.sparse_shape = keep
+        for i in range(stages):
+            batch_dict.update({
+                "encoded_spconv_tensor" + sid(i): self.decompose_tensor(out, i, bs),
+                "encoded_spconv_tensor_stride" + sid(i): 8,
+                "multi_scale_3d_features" + sid(i): {"x_conv1": None, "x_conv2": None,
+                                                    "x_conv3": self.decompose_tensor(ms["x_conv3"], i, bs),
+                                                    "x_conv4": self.decompose_tensor(ms["x_conv4"], i, bs)},
+                "multi_scale_3d_strides" + sid(i): dict(self._STRIDES)})
+        return batch_dict
+
+
+class HeightCompression(nn.Module):
+    """map_to_bev/height_compression.py:107-140 (dense + view; bev_align is off in every shipped
+    config).  ``nhwc=True`` writes the BEV map channels-last in one pass and returns it as a
+    (B, C*D, H, W) tensor in torch.channels_last memory format (same logical values)."""
+
+    def __init__(self, model_cfg=None, nhwc=True, **kwargs):
+        super().__init__()
+        self.model_cfg = _cfg(model_cfg)
+        self.num_bev_features = self.model_cfg.get("NUM_BEV_FEATURES", 256)
+        self.nhwc = nhwc
+
+    def forward(self, batch_dict):
+        stages = batch_dict["transform_param"].shape[1] if "transform_param" in batch_dict else 1
+        batch_dict["spatial_features_stride"] = batch_dict["encoded_spconv_tensor_stride"]
+        for i in range(stages):
+            sid = "" if i == 0 else str(i)
+            t = batch_dict["encoded_spconv_tensor" + sid]
+            if self.nhwc:
+                sf = t.dense_bev_nhwc().permute(0, 3, 1, 2)           # logical NCHW, channels_last strides
+            else:
+                d = t.dense()
+                n, c, dd, h, w = d.shape
+                sf = d.view(n, c * dd, h, w)
+            batch_dict["spatial_features" + sid] = sf
+        return batch_dict

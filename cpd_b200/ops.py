@@ -1,0 +1,293 @@
+"""Functional torch-level wrappers over the C ABI (device tensors in, device tensors out).
+
+torch is plumbing here: it owns device memory and the stream; all arithmetic happens in
+libcpd_b200.so.  Every function requires CUDA tensors and raises otherwise.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _i32x3(v):
+    if isinstance(v, int):
+        v = (v, v, v)
+    v = [int(x) for x in v]
+    assert len(v) == 3
+    return (C.c_int32 * 3)(*v)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.CpdError("cpd_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _f32c(t):
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.contiguous().float()
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------
+# voxelizer
+# ------------------------------------------------------------------------------------
+def voxelize(points, frame_offsets, pc_range, voxel_size, max_pts=5, max_voxels=1000000,
+             want_voxels=True, want_mean=True, cap_rows=None, sync=True):
+    """Batched Point2VoxelCPU3d + collate + MeanVFE (see include/cpd_b200.h).
+
+    points (N,C) float32 cuda, frames concatenated; frame_offsets: python ints, len batch+1.
+    Returns dict(voxels (M,max_pts,C) | None, coords (M,4) int32 [b,z,y,x], num (M,) int32,
+    mean (M,C) | None, counts (batch+1,) int32 device).  With sync=True tensors are sliced to
+    the true M (one D2H read of the counter, as any data-dependent shape needs); with
+    sync=False they keep cap_rows rows and `counts` stays on the device.
+    """
+    _need_cuda(points)
+    L = _lib.lib()
+    pts = _f32c(points)
+    n, c = pts.shape
+    batch = len(frame_offsets) - 1
+    dev = pts.device
+    if cap_rows is None:
+        cap_rows = int(min(n, batch * int(max_voxels)))
+    cap_rows = max(int(cap_rows), 1)
+    offs = (C.c_int64 * (batch + 1))(*[int(o) for o in frame_offsets])
+    rng = (C.c_float * 6)(*[float(v) for v in pc_range])
+    vs = (C.c_float * 3)(*[float(v) for v in voxel_size])
+    voxels = torch.empty((cap_rows, max_pts, c), dtype=torch.float32, device=dev) if want_voxels else None
+    mean = torch.empty((cap_rows, c), dtype=torch.float32, device=dev) if want_mean else None
+    coords = torch.empty((cap_rows, 4), dtype=torch.int32, device=dev)
+    num = torch.empty((cap_rows,), dtype=torch.int32, device=dev)
+    counts = torch.empty((batch + 1,), dtype=torch.int32, device=dev)
+    wsb = L.cpd_voxelize_workspace_bytes(n, batch, max_pts, cap_rows)
+    ws = _ws(wsb, dev)
+    _lib.check(L.cpd_voxelize(_ptr(pts), n, c, offs, batch, rng, vs, int(max_pts), int(max_voxels), cap_rows,
+                              _ptr(voxels), _ptr(coords), _ptr(num), _ptr(mean), _ptr(counts), _ptr(ws), wsb,
+                              _stream()), "cpd_voxelize")
+    out = dict(voxels=voxels, coords=coords, num=num, mean=mean, counts=counts)
+    if sync:
+        m = int(counts[batch].item())
+        if m > cap_rows:
+            raise _lib.CpdError(f"cpd_voxelize: {m} voxels exceed cap_rows={cap_rows}")
+        for k in ("voxels", "coords", "num", "mean"):
+            if out[k] is not None:
+                out[k] = out[k][:m]
+    return out
+
+
+# ------------------------------------------------------------------------------------
+# rulebooks
+# ------------------------------------------------------------------------------------
+def build_hash(coords, shape, batch):
+    _need_cuda(coords)
+    L = _lib.lib()
+    m = coords.shape[0]
+    nb = L.cpd_coord_hash_bytes(m)
+    h = torch.empty(nb, dtype=torch.uint8, device=coords.device)
+    _lib.check(L.cpd_coord_hash_build(_ptr(coords), m, _i32x3(shape), int(batch), _ptr(h), nb, _stream()),
+               "cpd_coord_hash_build")
+    return h
+
+
+def subm_table(coords, shape, batch, ksize, hash_buf):
+    _need_cuda(coords, hash_buf)
+    L = _lib.lib()
+    ks = _i32x3(ksize)
+    K = ks[0] * ks[1] * ks[2]
+    m = coords.shape[0]
+    nbr = torch.empty((m, K), dtype=torch.int32, device=coords.device)
+    _lib.check(L.cpd_rulebook_subm(_ptr(coords), m, _i32x3(shape), int(batch), ks, _ptr(hash_buf), hash_buf.numel(),
+                                   _ptr(nbr), _stream()), "cpd_rulebook_subm")
+    return nbr
+
+
+def strided_outputs(coords, shape, batch, ksize, stride, padding):
+    """-> (out_coords (M_out,4) int32 sorted by linear key, out_shape [D,H,W])."""
+    _need_cuda(coords)
+    L = _lib.lib()
+    ks, st, pd, sh = _i32x3(ksize), _i32x3(stride), _i32x3(padding), _i32x3(shape)
+    K = ks[0] * ks[1] * ks[2]
+    m = coords.shape[0]
+    dev = coords.device
+    wsb = L.cpd_rulebook_strided_workspace_bytes(sh, int(batch), ks, st, pd)
+    if wsb == 0:
+        raise _lib.CpdError("cpd_rulebook_strided: empty output shape")
+    ws = _ws(wsb, dev)
+    oshape = (C.c_int32 * 3)()
+    cap = max(m * min(K, 8), 1)
+    ocoords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    n_out = torch.empty((1,), dtype=torch.int32, device=dev)
+    _lib.check(L.cpd_rulebook_strided_outputs(_ptr(coords), m, sh, int(batch), ks, st, pd, oshape, cap, _ptr(ocoords),
+                                              _ptr(n_out), _ptr(ws), wsb, _stream()), "cpd_rulebook_strided_outputs")
+    mo = int(n_out.item())
+    if mo > cap:
+        raise _lib.CpdError("cpd_rulebook_strided_outputs: output capacity exceeded")
+    return ocoords[:mo], [int(oshape[0]), int(oshape[1]), int(oshape[2])]
+
+
+def strided_tables(in_coords, in_shape, in_hash, out_coords, out_shape, out_hash, batch, ksize, stride, padding,
+                   want_bwd=True):
+    _need_cuda(in_coords, out_coords)
+    L = _lib.lib()
+    ks, st, pd = _i32x3(ksize), _i32x3(stride), _i32x3(padding)
+    K = ks[0] * ks[1] * ks[2]
+    dev = in_coords.device
+    m_in, m_out = in_coords.shape[0], out_coords.shape[0]
+    fwd = torch.empty((m_out, K), dtype=torch.int32, device=dev)
+    bwd = torch.empty((m_in, K), dtype=torch.int32, device=dev) if want_bwd else None
+    _lib.check(L.cpd_rulebook_strided_tables(_ptr(in_coords), m_in, _i32x3(in_shape), _ptr(in_hash), in_hash.numel(),
+                                             _ptr(out_coords), m_out, _i32x3(out_shape),
+                                             _ptr(out_hash) if want_bwd else None,
+                                             out_hash.numel() if want_bwd else 0, int(batch), ks, st, pd,
+                                             _ptr(fwd), _ptr(bwd), _stream()), "cpd_rulebook_strided_tables")
+    return fwd, bwd
+
+
+def conv2d_table(n, h, w, kh, kw, stride, pad, transposed, ho, wo, device):
+    L = _lib.lib()
+    nbr = torch.empty((n * ho * wo, kh * kw), dtype=torch.int32, device=device)
+    _lib.check(L.cpd_conv2d_table(n, h, w, kh, kw, stride, pad, int(bool(transposed)), ho, wo, _ptr(nbr), _stream()),
+               "cpd_conv2d_table")
+    return nbr
+
+
+# ------------------------------------------------------------------------------------
+# gather-GEMM family
+# ------------------------------------------------------------------------------------
+ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05 = 0, 1, 2
+
+# bench.py sets this to a list to time every gather-GEMM launch with CUDA events on the
+# launching stream: entries are (start_event, end_event, meta dict holding the nbr table).
+PROFILE = None
+
+
+def gather_gemm(x, w, nbr, bias=None, scale=None, shift=None, residual=None, relu=False, stats=None,
+                algo=ALGO_AUTO, out=None):
+    """y[o] = epi(sum_k W[:,k,:] x[nbr[o,k]]);  w is (cout, K, cin) (any (cout, ..., cin) view)."""
+    _need_cuda(x, w, nbr)
+    L = _lib.lib()
+    x = _f32c(x)
+    cout, cin = w.shape[0], w.shape[-1]
+    w = _f32c(w).view(cout, -1, cin)
+    K = w.shape[1]
+    m_out = nbr.shape[0]
+    assert nbr.shape[1] == K and nbr.dtype == torch.int32 and nbr.is_contiguous()
+    assert x.shape[1] == cin
+    y = out if out is not None else torch.empty((m_out, cout), dtype=torch.float32, device=x.device)
+    residual = _f32c(residual) if residual is not None else None
+    wsb = L.cpd_gather_gemm_workspace_bytes(m_out, cin, K, cout, algo)
+    ws = _ws(wsb, x.device) if wsb else None
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.check(L.cpd_gather_gemm(_ptr(x), x.shape[0], cin, _ptr(w), K, cout, _ptr(nbr), m_out, _ptr(bias), _ptr(scale),
+                                 _ptr(shift), _ptr(residual), int(bool(relu)), _ptr(stats), _ptr(y), int(algo),
+                                 _ptr(ws), wsb, _stream()), "cpd_gather_gemm")
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append((e0, e1, dict(m_in=x.shape[0], m_out=m_out, cin=cin, cout=cout, K=K, nbr=nbr,
+                                     residual=residual is not None)))
+    return y
+
+
+def gather_wgrad(x, dy, nbr, want_bias=False):
+    """dw (cout, K, cin), dbias (cout,) | None."""
+    _need_cuda(x, dy, nbr)
+    L = _lib.lib()
+    x, dy = _f32c(x), _f32c(dy)
+    cin, cout, K = x.shape[1], dy.shape[1], nbr.shape[1]
+    dw = torch.empty((cout, K, cin), dtype=torch.float32, device=x.device)
+    db = torch.empty((cout,), dtype=torch.float32, device=x.device) if want_bias else None
+    _lib.check(L.cpd_gather_wgrad(_ptr(x), x.shape[0], cin, _ptr(dy), dy.shape[0], cout, _ptr(nbr), K, _ptr(dw), _ptr(db),
+                                  None, 0, _stream()), "cpd_gather_wgrad")
+    return dw, db
+
+
+def weight_transpose(w, flip_taps=False):
+    """(cout, K, cin) -> (cin, K, cout), optionally reversing taps."""
+    _need_cuda(w)
+    L = _lib.lib()
+    cout, cin = w.shape[0], w.shape[-1]
+    w = _f32c(w).view(cout, -1, cin)
+    K = w.shape[1]
+    wt = torch.empty((cin, K, cout), dtype=torch.float32, device=w.device)
+    _lib.check(L.cpd_weight_transpose(_ptr(w), cout, K, cin, int(bool(flip_taps)), _ptr(wt), _stream()),
+               "cpd_weight_transpose")
+    return wt
+
+
+def sparse_to_dense(feat, coords, batch, shape, channels_last=False):
+    _need_cuda(feat, coords)
+    L = _lib.lib()
+    feat = _f32c(feat)
+    m, c = feat.shape
+    d, h, w = [int(v) for v in shape]
+    if channels_last:
+        out = torch.empty((batch, h, w, c * d), dtype=torch.float32, device=feat.device)
+    else:
+        out = torch.empty((batch, c, d, h, w), dtype=torch.float32, device=feat.device)
+    _lib.check(L.cpd_sparse_to_dense(_ptr(feat), _ptr(coords), m, c, int(batch), _i32x3(shape), int(bool(channels_last)),
+                                     _ptr(out), _stream()), "cpd_sparse_to_dense")
+    return out
+
+
+def sparse_to_dense_bwd(dout, coords, c, batch, shape, channels_last=False):
+    _need_cuda(dout, coords)
+    L = _lib.lib()
+    dout = _f32c(dout)
+    m = coords.shape[0]
+    dfeat = torch.empty((m, c), dtype=torch.float32, device=dout.device)
+    _lib.check(L.cpd_sparse_to_dense_bwd(_ptr(dout), _ptr(coords), m, c, int(batch), _i32x3(shape),
+                                         int(bool(channels_last)), _ptr(dfeat), _stream()), "cpd_sparse_to_dense_bwd")
+    return dfeat
+
+
+# ------------------------------------------------------------------------------------
+# iou3d_nms
+# ------------------------------------------------------------------------------------
+def iou_bev(a, b, out=None, overlap=False):
+    _need_cuda(a, b)
+    L = _lib.lib()
+    a, b = _f32c(a), _f32c(b)
+    if out is None:
+        out = torch.zeros((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    fn = L.cpd_overlap_bev if overlap else L.cpd_iou_bev
+    _lib.check(fn(_ptr(a), a.shape[0], _ptr(b), b.shape[0], _ptr(out), _stream()), "cpd_iou_bev")
+    return out
+
+
+def nms(boxes_sorted, thresh, rotated=True):
+    """Greedy NMS over boxes sorted by descending score -> (keep int64 (n,) device, n_keep int32 (1,) device)."""
+    _need_cuda(boxes_sorted)
+    L = _lib.lib()
+    b = _f32c(boxes_sorted)
+    n = b.shape[0]
+    keep = torch.empty((max(n, 1),), dtype=torch.int64, device=b.device)
+    n_keep = torch.zeros((1,), dtype=torch.int32, device=b.device)
+    wsb = L.cpd_nms_workspace_bytes(n)
+    ws = _ws(wsb, b.device)
+    fn = L.cpd_nms_rotated if rotated else L.cpd_nms_normal
+    _lib.check(fn(_ptr(b), n, float(thresh), _ptr(keep), _ptr(n_keep), _ptr(ws), wsb, _stream()), "cpd_nms")
+    return keep, n_keep
+
+
+def nms_mask(boxes_sorted, thresh, rotated=True):
+    _need_cuda(boxes_sorted)
+    L = _lib.lib()
+    b = _f32c(boxes_sorted)
+    n = b.shape[0]
+    cb = (n + 63) // 64
+    mask = torch.zeros((n, cb), dtype=torch.int64, device=b.device)
+    _lib.check(L.cpd_nms_mask(_ptr(b), n, float(thresh), int(bool(rotated)), _ptr(mask), _stream()), "cpd_nms_mask")
+    return mask

@@ -1,0 +1,288 @@
+"""spconv-compatible sparse tensor and convolution modules on top of libcpd_b200.so.
+
+Mirrors the third-party surface the reference consumes:
+``SparseConvTensor``, ``SparseModule``, ``SparseSequential``, ``SubMConv3d``,
+``SparseConv3d``, ``SparseInverseConv3d`` (constructible, no forward -- never requested by
+the reference, cpd/models/backbones_3d/spconv_backbone.py:24) and
+``conv.SparseConvolution`` (cpd/utils/spconv_utils.py:49).  Weights are exposed in the
+spconv 2.x layout (cout, kz, ky, kx, cin) so CPD checkpoints load through
+cpd/models/detectors/detector3d_template.py:388-419 unchanged.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def _triple(v):
+    if isinstance(v, (list, tuple, np.ndarray)):
+        assert len(v) == 3
+        return [int(t) for t in v]
+    return [int(v)] * 3
+
+
+class Rulebook:
+    """Cached per indice_key, like spconv's indice_dict entries."""
+
+    def __init__(self, kind, nbr_fwd, nbr_bwd, in_coords, out_coords, in_shape, out_shape, ksize, stride, padding):
+        self.kind = kind                    # 'subm' | 'strided'
+        self.nbr_fwd = nbr_fwd              # (m_out, K) int32
+        self.nbr_bwd = nbr_bwd              # strided: (m_in, K); subm: None (same table, flipped taps)
+        self.in_coords, self.out_coords = in_coords, out_coords
+        self.in_shape, self.out_shape = in_shape, out_shape
+        self.ksize, self.stride, self.padding = ksize, stride, padding
+        self.out_hash = None                # coordinate hash of out_coords (strided only)
+
+
+class SparseConvTensor:
+    """features (N,C) float32; indices (N,4) int32 [batch,z,y,x]; spatial_shape [D,H,W]."""
+
+    def __init__(self, features, indices, spatial_shape, batch_size, grid=None, voxel_num=None, indice_dict=None,
+                 benchmark=False):
+        self.features = features
+        self.indices = indices if indices.dtype == torch.int32 else indices.int()
+        if not self.indices.is_contiguous():
+            self.indices = self.indices.contiguous()
+        self.spatial_shape = [int(s) for s in spatial_shape]   # accepts a numpy int64 array (spconv_backbone.py:151)
+        self.batch_size = int(batch_size)
+        self.indice_dict = indice_dict if indice_dict is not None else {}
+        self._hash = None                                      # coordinate hash of `indices` (lazily built)
+        self.grid, self.voxel_num, self.benchmark = grid, voxel_num, benchmark
+
+    # -- spconv 2.x API -------------------------------------------------------------
+    def replace_feature(self, feature):
+        t = SparseConvTensor(feature, self.indices, self.spatial_shape, self.batch_size, self.grid, self.voxel_num,
+                             self.indice_dict, self.benchmark)
+        t._hash = self._hash
+        return t
+
+    @property
+    def spatial_size(self):
+        return int(np.prod(self.spatial_shape))
+
+    def find_indice_pair(self, key):
+        return None if key is None else self.indice_dict.get(key)
+
+    def coord_hash(self):
+        if self._hash is None:
+            self._hash = ops.build_hash(self.indices, self.spatial_shape, self.batch_size)
+        return self._hash
+
+    def dense(self, channels_first=True):
+        """(B, C, D, H, W) like upstream; channels_first=False gives (B, D, H, W, C)."""
+        out = _ToDense.apply(self.features, self.indices, self.batch_size, tuple(self.spatial_shape), False)
+        return out if channels_first else out.permute(0, 2, 3, 4, 1).contiguous()
+
+    def dense_bev_nhwc(self):
+        """(B, H, W, C*D): the NHWC form of HeightCompression's (B, C*D, H, W) map
+        (cpd/models/backbones_2d/map_to_bev/height_compression.py:136-138), written in one pass."""
+        return _ToDense.apply(self.features, self.indices, self.batch_size, tuple(self.spatial_shape), True)
+
+
+class _ToDense(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, coords, batch, shape, channels_last):
+        ctx.save_for_backward(coords)
+        ctx.meta = (feat.shape[1], batch, shape, channels_last)
+        return ops.sparse_to_dense(feat, coords, batch, shape, channels_last)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (coords,) = ctx.saved_tensors
+        c, batch, shape, cl = ctx.meta
+        return ops.sparse_to_dense_bwd(dout.contiguous(), coords, c, batch, shape, cl), None, None, None, None
+
+
+class _GatherConv(torch.autograd.Function):
+    """y = gather-GEMM(x, W, nbr) (+bias); backward = dgrad gather-GEMM + wgrad (Appendix A.5)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, rb, algo):
+        ctx.rb, ctx.algo = rb, algo
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return ops.gather_gemm(x, weight, rb.nbr_fwd, bias=bias, algo=algo)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        rb = ctx.rb
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            if rb.kind == "subm":
+                wt = ops.weight_transpose(weight, flip_taps=True)
+                dx = ops.gather_gemm(dy, wt, rb.nbr_fwd, algo=ctx.algo)
+            else:
+                wt = ops.weight_transpose(weight, flip_taps=False)
+                dx = ops.gather_gemm(dy, wt, rb.nbr_bwd, algo=ctx.algo)
+        if ctx.needs_input_grad[1] or ctx.has_bias:
+            dw, db = ops.gather_wgrad(x, dy, rb.nbr_fwd, want_bias=ctx.has_bias)
+            dw = dw.view_as(weight)
+        return dx, dw, db, None, None
+
+
+class SparseModule(nn.Module):
+    """Marker base class: modules that consume/produce SparseConvTensor."""
+
+
+class SparseConvolution(SparseModule):
+    def __init__(self, ndim, in_channels, out_channels, kernel_size=3, stride=1, padding=0, dilation=1, groups=1,
+                 bias=True, subm=False, output_padding=0, transposed=False, inverse=False, indice_key=None,
+                 algo=None, **kwargs):
+        super().__init__()
+        assert ndim == 3 and groups == 1
+        assert _triple(dilation) == [1, 1, 1], "dilation is not used by the CPD backbones"
+        self.ndim, self.in_channels, self.out_channels = ndim, in_channels, out_channels
+        self.kernel_size, self.stride, self.padding = _triple(kernel_size), _triple(stride), _triple(padding)
+        self.subm, self.inverse, self.transposed = subm, inverse, transposed
+        self.indice_key = indice_key
+        self.algo = ops.ALGO_AUTO if algo is None else algo
+        self.weight = nn.Parameter(torch.empty(out_channels, *self.kernel_size, in_channels))
+        self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            fan_in = self.in_channels * int(np.prod(self.kernel_size))
+            bound = 1 / math.sqrt(fan_in)
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def extra_repr(self):
+        return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, "
+                f"padding={self.padding}, subm={self.subm}, indice_key={self.indice_key}")
+
+    # -- rulebook ---------------------------------------------------------------------
+    def get_rulebook(self, inp):
+        rb = inp.find_indice_pair(self.indice_key)
+        if rb is not None and rb.kind == ("subm" if self.subm else "strided") and rb.in_coords is inp.indices \
+                and rb.ksize == self.kernel_size:
+            return rb, rb.out_hash
+        out_hash = None
+        if self.subm:
+            nbr = ops.subm_table(inp.indices, inp.spatial_shape, inp.batch_size, self.kernel_size, inp.coord_hash())
+            rb = Rulebook("subm", nbr, None, inp.indices, inp.indices, inp.spatial_shape, inp.spatial_shape,
+                          self.kernel_size, [1, 1, 1], [0, 0, 0])
+        else:
+            ocoords, oshape = ops.strided_outputs(inp.indices, inp.spatial_shape, inp.batch_size, self.kernel_size,
+                                                  self.stride, self.padding)
+            ocoords = ocoords.clone() if ocoords.storage_offset() else ocoords  # keep 16 B alignment
+            out_hash = ops.build_hash(ocoords, oshape, inp.batch_size)
+            fwd, bwd = ops.strided_tables(inp.indices, inp.spatial_shape, inp.coord_hash(), ocoords, oshape, out_hash,
+                                          inp.batch_size, self.kernel_size, self.stride, self.padding, want_bwd=True)
+            rb = Rulebook("strided", fwd, bwd, inp.indices, ocoords, inp.spatial_shape, oshape, self.kernel_size,
+                          self.stride, self.padding)
+            rb.out_hash = out_hash
+        if self.indice_key is not None:
+            inp.indice_dict[self.indice_key] = rb
+        return rb, out_hash
+
+    def _wrap_output(self, inp, rb, out_hash, feats):
+        if self.subm:
+            return inp.replace_feature(feats)
+        out = SparseConvTensor(feats, rb.out_coords, rb.out_shape, inp.batch_size, inp.grid, inp.voxel_num,
+                               inp.indice_dict, inp.benchmark)
+        out._hash = out_hash
+        return out
+
+    def forward(self, inp):
+        if self.inverse or self.transposed:
+            raise NotImplementedError("SparseInverseConv3d forward is not part of the CPD hot path")
+        rb, out_hash = self.get_rulebook(inp)
+        feats = _GatherConv.apply(inp.features, self.weight, self.bias, rb, self.algo)
+        return self._wrap_output(inp, rb, out_hash, feats)
+
+    def forward_fused(self, inp, scale, shift, relu, residual=None):
+        """Inference-only: conv + folded BatchNorm affine (+ residual) (+ ReLU) in one kernel."""
+        rb, out_hash = self.get_rulebook(inp)
+        feats = ops.gather_gemm(inp.features, self.weight, rb.nbr_fwd, bias=self.bias, scale=scale, shift=shift,
+                                residual=residual, relu=relu, algo=self.algo)
+        return self._wrap_output(inp, rb, out_hash, feats)
+
+
+class SubMConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None, algo=None, **kwargs):
+        super().__init__(3, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, True,
+                         indice_key=indice_key, algo=algo)
+
+
+class SparseConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None, algo=None, **kwargs):
+        super().__init__(3, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, False,
+                         indice_key=indice_key, algo=algo)
+
+
+class SparseInverseConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, indice_key=None, bias=True, algo=None, **kwargs):
+        super().__init__(3, in_channels, out_channels, kernel_size, bias=bias, inverse=True, indice_key=indice_key,
+                         algo=algo)
+
+
+def fold_bn(bn):
+    """eval-mode BatchNorm -> per-channel (scale, shift) float32 tensors."""
+    inv = torch.rsqrt(bn.running_var.float() + bn.eps)
+    g = bn.weight.float() if bn.weight is not None else torch.ones_like(inv)
+    b = bn.bias.float() if bn.bias is not None else torch.zeros_like(inv)
+    scale = (g * inv).contiguous()
+    shift = (b - bn.running_mean.float() * g * inv).contiguous()
+    return scale, shift
+
+
+class SparseSequential(SparseModule):
+    """nn.Sequential that threads SparseConvTensor through sparse modules and applies dense
+    layers (BatchNorm1d, ReLU, ...) to ``.features`` (spconv_backbone.py:29,153-193).
+    In eval mode ``conv -> BatchNorm1d -> ReLU`` runs as ONE kernel (folded affine epilogue)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        if len(args) == 1 and isinstance(args[0], dict):
+            for k, m in args[0].items():
+                self.add_module(k, m)
+        else:
+            for i, m in enumerate(args):
+                self.add_module(str(i), m)
+        for k, m in kwargs.items():
+            self.add_module(k, m)
+
+    def __getitem__(self, idx):
+        return list(self._modules.values())[idx]
+
+    def __len__(self):
+        return len(self._modules)
+
+    def add(self, module, name=None):
+        self.add_module(name if name is not None else str(len(self._modules)), module)
+
+    def forward(self, x):
+        mods = list(self._modules.values())
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if not self.training and not torch.is_grad_enabled() \
+                    and isinstance(m, SparseConvolution) and not m.inverse and isinstance(x, SparseConvTensor) \
+                    and i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d):
+                relu = i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)
+                scale, shift = fold_bn(mods[i + 1])
+                x = m.forward_fused(x, scale, shift, relu)
+                i += 3 if relu else 2
+                continue
+            if isinstance(m, SparseModule):
+                x = m(x)
+            elif isinstance(x, SparseConvTensor):
+                if x.indices.shape[0] != 0:
+                    x = x.replace_feature(m(x.features))
+            else:
+                x = m(x)
+            i += 1
+        return x
+
+
+class ToDense(SparseModule):
+    def forward(self, x):
+        return x.dense()

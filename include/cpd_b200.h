@@ -1,0 +1,193 @@
+/*
+ * cpd_b200.h -- C ABI of libcpd_b200.so: the B200-native (sm_100a) implementation of
+ * the CPD detection hot path (voxelizer -> sparse-3D-conv backbone -> BEV head -> NMS).
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless the
+ *     parameter name ends in _host; fp32 features, int32 indices, row-major;
+ *   - the caller owns every buffer, including workspaces (query *_workspace_bytes);
+ *     the library never allocates device memory and never synchronises the device;
+ *   - every entry takes the CUDA stream to launch on and is graph-capturable;
+ *   - every entry returns int32 status: 0 = ok, <0 = cpd_status; nothing ever calls
+ *     exit() or throws across the boundary (the reference does: iou3d_nms.cpp:14-38);
+ *   - data-dependent output sizes are returned through device counters that the host
+ *     reads when it needs them (two-phase calls).
+ *
+ * Each entry cites the reference interface it replaces (paths relative to the
+ * hailanyi/CPD tree).  INTEGRATION.md shows the Python-side binding.
+ */
+#ifndef CPD_B200_H_
+#define CPD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CPD_API __attribute__((visibility("default")))
+#else
+#define CPD_API
+#endif
+
+typedef void *cpd_stream_t; /* cudaStream_t */
+
+enum cpd_status {
+    CPD_OK = 0,
+    CPD_ERR_BAD_ARG = -1,
+    CPD_ERR_MISALIGNED = -2,
+    CPD_ERR_WORKSPACE = -3, /* workspace too small */
+    CPD_ERR_UNSUPPORTED = -4,
+    CPD_ERR_CUDA = -100 /* CUDA error; cpd_last_error_string() has the text */
+};
+
+#define CPD_MAX_BATCH 64
+
+CPD_API int32_t cpd_version(void);
+CPD_API const char *cpd_last_error_string(void);
+/* number of kernels this library has launched in this process (bench.py: gpu_launches) */
+CPD_API int64_t cpd_launch_count(void);
+
+/* ---------------------------------------------------------------------------------
+ * Voxelizer.  Replaces spconv.utils.Point2VoxelCPU3d.point_to_voxel as called from
+ * cpd/datasets/processor/data_processor.py:35-41,53-58 (VoxelGeneratorWrapper) for a
+ * whole batch at once, including collate_batch's batch-index column
+ * (cpd/datasets/dataset.py:262-266) and, optionally, MeanVFE
+ * (cpd/models/backbones_3d/vfe/mean_vfe.py:41-50).
+ *
+ * points: (n_points, c) fp32, frames concatenated; frame f owns rows
+ * [frame_offsets_host[f], frame_offsets_host[f+1]).  Voxel rows come out frame-major,
+ * inside a frame in order of first appearance, each keeping its first max_pts points
+ * in input order -- bit-identical to the sequential reference.
+ * counts: (batch+1,) int32 device: voxels kept per frame, [batch] = total rows.
+ * mean may be NULL.  voxels may be NULL (mean-only mode).
+ * --------------------------------------------------------------------------------- */
+CPD_API size_t cpd_voxelize_workspace_bytes(int64_t n_points, int32_t batch, int32_t max_pts, int64_t cap_rows);
+CPD_API int32_t cpd_voxelize(const float *points, int64_t n_points, int32_t c,
+                     const int64_t *frame_offsets_host, int32_t batch,
+                     const float *range6_host, const float *vsize3_host,
+                     int32_t max_pts, int64_t max_voxels, int64_t cap_rows,
+                     float *voxels, int32_t *coords_bzyx, int32_t *num_points, float *mean,
+                     int32_t *counts, void *ws, size_t ws_bytes, cpd_stream_t stream);
+
+/* ---------------------------------------------------------------------------------
+ * Rulebooks.  Replace the indice-pair generation hidden inside spconv.SubMConv3d /
+ * spconv.SparseConv3d (call sites cpd/models/backbones_3d/spconv_backbone.py:17,20-21,
+ * 108-115,189-190,415,451-452), cached per indice_key like upstream.
+ *
+ * Layout is output-stationary: nbr[(row, tap)] = input row feeding `row` through
+ * tap = (kz*KH+ky)*KW+kx, or -1.  coords: (m,4) int32 [b,z,y,x].
+ * --------------------------------------------------------------------------------- */
+CPD_API size_t cpd_coord_hash_bytes(int64_t m);
+CPD_API int32_t cpd_coord_hash_build(const int32_t *coords, int64_t m, const int32_t *shape3_host,
+                             int32_t batch, void *hash, size_t hash_bytes, cpd_stream_t stream);
+
+/* SubMConv3d: output sites == input sites; input site = site + tap - ksize/2. */
+CPD_API int32_t cpd_rulebook_subm(const int32_t *coords, int64_t m, const int32_t *shape3_host, int32_t batch,
+                          const int32_t *ksize3_host, const void *hash, size_t hash_bytes,
+                          int32_t *nbr, cpd_stream_t stream);
+
+/* SparseConv3d, phase 1: active output set, rows in ascending linear key
+ * ((b*D+z)*H+y)*W+x.  out_shape3_host is written on return (host arithmetic);
+ * n_out: int32 device counter (rows beyond cap_out are dropped and n_out still
+ * reports the true count so the caller can detect overflow). */
+CPD_API size_t cpd_rulebook_strided_workspace_bytes(const int32_t *shape3_host, int32_t batch,
+                                            const int32_t *ksize3_host, const int32_t *stride3_host,
+                                            const int32_t *pad3_host);
+CPD_API int32_t cpd_rulebook_strided_outputs(const int32_t *coords, int64_t m, const int32_t *shape3_host,
+                                     int32_t batch, const int32_t *ksize3_host,
+                                     const int32_t *stride3_host, const int32_t *pad3_host,
+                                     int32_t *out_shape3_host, int64_t cap_out, int32_t *out_coords,
+                                     int32_t *n_out, void *ws, size_t ws_bytes, cpd_stream_t stream);
+/* phase 2: nbr_fwd (m_out, K): input row feeding output o through tap k;
+ *          nbr_bwd (m_in, K): output row fed by input i through tap k (may be NULL). */
+CPD_API int32_t cpd_rulebook_strided_tables(const int32_t *in_coords, int64_t m_in, const int32_t *in_shape3_host,
+                                    const void *in_hash, size_t in_hash_bytes,
+                                    const int32_t *out_coords, int64_t m_out, const int32_t *out_shape3_host,
+                                    const void *out_hash, size_t out_hash_bytes, int32_t batch,
+                                    const int32_t *ksize3_host, const int32_t *stride3_host,
+                                    const int32_t *pad3_host, int32_t *nbr_fwd, int32_t *nbr_bwd,
+                                    cpd_stream_t stream);
+
+/* ---------------------------------------------------------------------------------
+ * Gather-GEMM ("implicit GEMM over a neighbour table"): the arithmetic of
+ * spconv.SubMConv3d / SparseConv3d forward and input-gradient, and -- with a table
+ * generated on the fly from the image geometry -- of the dense BEV convolutions.
+ *
+ *   y[o, :] = epilogue( sum_k  W[:, k, :] . x[nbr[o, k], :] )      nbr == -1 -> zero row
+ *
+ * w: (cout, K, cin) fp32 = spconv 2.x layout (cout, kz, ky, kx, cin)
+ *    (cpd/models/detectors/detector3d_template.py:399-408).
+ * epilogue: + bias[cout] (NULL ok); * scale[cout] + shift[cout] (NULL ok: folded
+ * eval-mode BatchNorm, spconv_backbone.py:410); + residual[o,:] (NULL ok:
+ * SparseBasicBlock, spconv_backbone.py:100-136); ReLU if relu != 0.
+ * stats (NULL ok): (2, cout) fp32 accumulators receiving per-channel sum and sum of
+ * squares of the pre-affine output (training-mode BatchNorm statistics).
+ * --------------------------------------------------------------------------------- */
+enum cpd_gemm_algo { CPD_ALGO_AUTO = 0, CPD_ALGO_SIMT = 1, CPD_ALGO_TCGEN05 = 2 };
+
+CPD_API int32_t cpd_gather_gemm(const float *x, int64_t m_in, int32_t cin, const float *w, int32_t K, int32_t cout,
+                        const int32_t *nbr, int64_t m_out, const float *bias, const float *scale,
+                        const float *shift, const float *residual, int32_t relu, float *stats, float *y,
+                        int32_t algo, void *ws, size_t ws_bytes, cpd_stream_t stream);
+CPD_API size_t cpd_gather_gemm_workspace_bytes(int64_t m_out, int32_t cin, int32_t K, int32_t cout, int32_t algo);
+
+/* Weight-gradient: dw[co, k, ci] = sum_o dy[o, co] * x[nbr[o, k], ci]; dw is overwritten.
+ * dbias (NULL ok): dbias[co] = sum_o dy[o, co]. */
+CPD_API int32_t cpd_gather_wgrad(const float *x, int64_t m_in, int32_t cin, const float *dy, int64_t m_out,
+                         int32_t cout, const int32_t *nbr, int32_t K, float *dw, float *dbias,
+                         void *ws, size_t ws_bytes, cpd_stream_t stream);
+CPD_API size_t cpd_gather_wgrad_workspace_bytes(int64_t m_out, int32_t cin, int32_t K, int32_t cout);
+
+/* (cout, K, cin) -> (cin, K, cout), optionally reversing the tap order (the operand of
+ * the input-gradient: SubM reuses its own table with flipped taps). */
+CPD_API int32_t cpd_weight_transpose(const float *w, int32_t cout, int32_t K, int32_t cin, int32_t flip_taps,
+                             float *wt, cpd_stream_t stream);
+
+/* Neighbour table of a dense 2-D convolution over an NHWC image batch (n, h, w, c):
+ * rows are pixels ((n*ho + y)*wo + x), taps (ky*kw + kx); replaces cuDNN's implicit
+ * addressing for nn.Conv2d in cpd/models/backbones_2d/base_bev_backbone.py:31-47 and
+ * cpd/models/dense_heads/center_head.py:11-45,73-80.  transposed != 0 builds the table
+ * of the input-gradient / of nn.ConvTranspose2d (base_bev_backbone.py:48-59). */
+CPD_API int32_t cpd_conv2d_table(int32_t n, int32_t h, int32_t w, int32_t kh, int32_t kw, int32_t stride,
+                         int32_t pad, int32_t transposed, int32_t ho, int32_t wo, int32_t *nbr,
+                         cpd_stream_t stream);
+
+/* SparseConvTensor.dense() fused with HeightCompression's view
+ * (cpd/models/backbones_2d/map_to_bev/height_compression.py:136-138): scatter (m, c)
+ * rows into a zeroed image.  channels_last == 0: out is (B, C, D, H, W) as upstream;
+ * channels_last != 0: out is (B, H, W, C*D) with channel index c*D + z, i.e. the NHWC
+ * form of the (B, C*D, H, W) BEV map.  The _bwd entry gathers the gradient back. */
+CPD_API int32_t cpd_sparse_to_dense(const float *feat, const int32_t *coords, int64_t m, int32_t c, int32_t batch,
+                            const int32_t *shape3_host, int32_t channels_last, float *out, cpd_stream_t stream);
+CPD_API int32_t cpd_sparse_to_dense_bwd(const float *dout, const int32_t *coords, int64_t m, int32_t c, int32_t batch,
+                                const int32_t *shape3_host, int32_t channels_last, float *dfeat,
+                                cpd_stream_t stream);
+
+/* ---------------------------------------------------------------------------------
+ * iou3d_nms.  Replace cpd/ops/iou3d_nms/src/iou3d_nms.h:9-12 (boxes_overlap_bev_gpu,
+ * boxes_iou_bev_gpu, nms_gpu, nms_normal_gpu).  boxes: (n,7) fp32
+ * [x,y,z,dx,dy,dz,heading].  NMS expects rows sorted by descending score, like the
+ * reference (iou3d_nms_utils.py:111-115); keep (n,) int64 and n_keep (1,) int32 are
+ * DEVICE buffers -- the reference's blocking D2H mask copy + host scan
+ * (iou3d_nms.cpp:103-132) is replaced by an on-device scan.
+ * --------------------------------------------------------------------------------- */
+CPD_API int32_t cpd_overlap_bev(const float *a, int32_t na, const float *b, int32_t nb, float *out, cpd_stream_t stream);
+CPD_API int32_t cpd_iou_bev(const float *a, int32_t na, const float *b, int32_t nb, float *out, cpd_stream_t stream);
+CPD_API size_t cpd_nms_workspace_bytes(int32_t n);
+CPD_API int32_t cpd_nms_rotated(const float *boxes, int32_t n, float thresh, int64_t *keep, int32_t *n_keep,
+                        void *ws, size_t ws_bytes, cpd_stream_t stream);
+CPD_API int32_t cpd_nms_normal(const float *boxes, int32_t n, float thresh, int64_t *keep, int32_t *n_keep,
+                       void *ws, size_t ws_bytes, cpd_stream_t stream);
+/* the suppression bit-matrix alone (n x ceil(n/64) uint64, upper-triangle tiles; tiles
+ * below the diagonal are zero -- the reference computes them but never reads them,
+ * iou3d_nms.cpp:128) -- exposed for parity tests against the reference kernel. */
+CPD_API int32_t cpd_nms_mask(const float *boxes, int32_t n, float thresh, int32_t rotated, uint64_t *mask,
+                     cpd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPD_B200_H_ */
