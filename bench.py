@@ -244,11 +244,11 @@ def cpu_baseline(a, frames, net=None):
         net = make_net(torch.device("cpu"))
     cores = os.cpu_count() or 1
     O.set_threads(cores)
-    pipeline.backbone_forward(net, [frames[0][:20000]], PC_RANGE, VOXEL_SIZE)      # warm caches / page in
+    pipeline.backbone_forward(net, [frames[0][:20000]], PC_RANGE, VOXEL_SIZE, eval_wide=True)      # warm caches / page in
     t0 = time.perf_counter()
     n = 0
     while True:
-        feats, coords, shape, _ = pipeline.backbone_forward(net, [frames[n % len(frames)]], PC_RANGE, VOXEL_SIZE)
+        feats, coords, shape, _ = pipeline.backbone_forward(net, [frames[n % len(frames)]], PC_RANGE, VOXEL_SIZE, eval_wide=True)
         pipeline.bev_dense(feats, coords, 1, shape)
         n += 1
         dt = time.perf_counter() - t0

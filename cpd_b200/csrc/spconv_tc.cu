@@ -1,14 +1,332 @@
-// tcgen05 gather-GEMM (placeholder until the tensor-core kernel lands; reports unsupported
-// so that CPD_ALGO_AUTO resolves to the SIMT kernel and CPD_ALGO_TCGEN05 fails loudly).
+// tcgen05 gather-GEMM for sm_100a: y[o,:] = epi( sum_k W[:,k,:] x[nbr[o,k],:] ) with fp32-class
+// accuracy on the 5th-generation tensor cores (3xTF32 operand splitting).
+//
+// Serves spconv.SubMConv3d / SparseConv3d forward + input-gradient (call sites
+// cpd/models/backbones_3d/spconv_backbone.py:17,20-21,108-115) and, through cpd_conv2d_table,
+// the dense BEV convolutions (cpd/models/backbones_2d/base_bev_backbone.py:31-59,
+// cpd/models/dense_heads/center_head.py:11-45,73-80).
+//
+// One CTA = 128 output rows x all BN = C_out columns, accumulator in TMEM (BN columns).
+//   warps 0-3  producers: gather A rows (x[nbr[o,k]], 128 B per row per k-block) and the
+//              W[:,k,c0:c0+32] slab straight from global/L2 with 16-byte loads, split every
+//              fp32 into tf32 hi + lo parts in registers and store both into shared memory in
+//              the canonical K-major SWIZZLE_128B layout that UMMA descriptors address
+//              (gathered rows are not TMA-tileable; the split has to pass through registers
+//              anyway).  fence.proxy.async + mbarrier arrive hand the stage to the MMA warp.
+//              Taps for which no row of the tile has a neighbour are skipped altogether.
+//   warp 4     allocates TMEM, then one elected lane issues per k-block 4 x 3
+//              tcgen05.mma.cta_group::1.kind::tf32 (A_hi.B_hi + A_lo.B_hi + A_hi.B_lo, M=128,
+//              N=BN, K=8) and tcgen05.commit's the stage back to the producers.
+//   warps 0-3  epilogue: tcgen05.ld the accumulator (lane = row), + bias, stage through shared
+//              memory (padded rows, conflict-free), then coalesced float4 stores with the folded
+//              BatchNorm affine / residual / ReLU applied on the way out and per-channel
+//              sum / sum-of-squares taken from the staged tile.
+//
+// TF32 keeps 10 mantissa bits: a single-pass product would miss the 1e-4 parity bar
+// (SURVEY.md H4); hi = x & 0xffffe000, lo = x - hi (exact) restores ~2^-21 relative error.
 #include "common.cuh"
+
 namespace cpd {
-bool gather_gemm_tc_supported(int32_t, int32_t, int32_t) { return false; }
-size_t gather_gemm_tc_workspace(int64_t, int32_t, int32_t, int32_t) { return 0; }
-int32_t gather_gemm_tc(const float *, int64_t, int32_t, const float *, int32_t, int32_t, const int32_t *, int64_t,
-                       const float *, const float *, const float *, const float *, int32_t, float *, float *, void *,
-                       size_t, cudaStream_t)
+namespace {
+
+constexpr int BM = 128;       // UMMA M
+constexpr int BK = 32;        // fp32 per k-block = 128 bytes = one swizzle row
+constexpr int NPROD = 128;    // producer / epilogue threads (warps 0..3)
+constexpr int NTHREADS = 160; // + MMA warp
+constexpr int MAX_TAPS = 32;
+
+__host__ __device__ constexpr int stages_for(int bn) { return bn >= 256 ? 2 : bn >= 128 ? 3 : 2; }
+__host__ __device__ constexpr int stage_bytes(int bn) { return 2 * BM * BK * 4 + 2 * bn * BK * 4; }
+__host__ __device__ constexpr int tmem_cols(int bn) { return bn < 32 ? 32 : bn; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    set_error("tcgen05 gather-GEMM not built");
-    return CPD_ERR_UNSUPPORTED;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc),
+        "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major, SWIZZLE_128B, 8-row groups 1024 B apart (SBO), LBO unused (=1), descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
+{
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// byte offset of 16-byte chunk c (0..7) of row r inside a [rows x 128 B] swizzled tile
+__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
+
+__device__ __forceinline__ void split_store(uint8_t *hi_tile, uint8_t *lo_tile, uint32_t off, float4 v)
+{
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+    *reinterpret_cast<float4 *>(hi_tile + off) = h;
+    *reinterpret_cast<float4 *>(lo_tile + off) = l;
+}
+
+struct TcArgs {
+    const float *x, *w, *bias, *scale, *shift, *residual;
+    const int32_t *nbr;
+    float *stats, *y;
+    long long m_out;
+    int cin, K, cout, relu;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
+{
+    constexpr int STAGES = stages_for(BN);
+    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE = stage_bytes(BN);
+    constexpr int OUT_LD = BN + 4;   // padded staging row (floats): conflict-free 16-byte stores
+    static_assert(BM * OUT_LD * 4 <= STAGES * STAGE, "epilogue staging must fit in the pipeline buffers");
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    int32_t *nbr_s = reinterpret_cast<int32_t *>(tiles + STAGES * STAGE);          // [K][BM]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(nbr_s + a.K * BM);              // full[S], empty[S], accum
+    uint32_t *misc = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);         // [0] tmem base, [1] tap mask
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum_bar = smem_u32(bars + 2 * STAGES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long row0 = (long long)blockIdx.x * BM;
+
+    if (tid == 0) misc[1] = 0u;
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, NPROD); mbar_init(empty0 + 8 * s, 1); }
+            mbar_init(accum_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(misc)), "r"(tmem_cols(BN)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    __syncthreads();
+    if (warp < 4) {   // neighbour tile -> smem, and the set of taps that have any work in this tile
+        const long long row = row0 + tid;
+        uint32_t mine = 0u;
+        for (int k = 0; k < a.K; ++k) {
+            int32_t idx = row < a.m_out ? __ldg(a.nbr + row * a.K + k) : -1;
+            nbr_s[k * BM + tid] = idx;
+            if (idx >= 0) mine |= 1u << k;
+        }
+        mine = __reduce_or_sync(0xffffffffu, mine);
+        if (lane == 0 && mine) atomicOr(&misc[1], mine);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = misc[0];
+    const uint32_t tap_mask = misc[1];
+    const int kblocks = (a.cin + BK - 1) / BK;
+    const int n_iters = __popc(tap_mask) * kblocks;
+
+    if (warp < 4) {
+        // ================= producers =================
+        const int c = tid & 7, r_base = tid >> 3;   // 16-byte chunk, first row (rows r_base + 16 j)
+        int it = 0;
+        for (int k = 0; k < a.K; ++k) {
+            if (!((tap_mask >> k) & 1u)) continue;
+            for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                const int s = it % STAGES;
+                const int col = kb * BK + c * 4;
+                const bool col_ok = col < a.cin;
+                float4 av[BM / 16], bv[BN / 16];
+#pragma unroll
+                for (int j = 0; j < BM / 16; ++j) {
+                    const int32_t idx = nbr_s[k * BM + r_base + 16 * j];
+                    av[j] = (idx >= 0 && col_ok) ? __ldg(reinterpret_cast<const float4 *>(a.x + (size_t)idx * a.cin + col))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < BN / 16; ++j) {
+                    const int n = r_base + 16 * j;
+                    bv[j] = col_ok ? __ldg(reinterpret_cast<const float4 *>(a.w + ((size_t)n * a.K + k) * a.cin + col))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
+                uint8_t *st = tiles + s * STAGE;
+#pragma unroll
+                for (int j = 0; j < BM / 16; ++j) split_store(st, st + A_BYTES, swz(r_base + 16 * j, c), av[j]);
+#pragma unroll
+                for (int j = 0; j < BN / 16; ++j) split_store(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, swz(r_base + 16 * j, c), bv[j]);
+                fence_async_smem();
+                mbar_arrive(full0 + 8 * s);
+            }
+        }
+        // ================= epilogue =================
+        float *stage_out = reinterpret_cast<float *>(tiles);
+        if (n_iters > 0) {
+            mbar_wait(accum_bar, 0);
+            tc_fence_after();
+        }
+        const int my_row = warp * 32 + lane;
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t v[16];
+            if (n_iters > 0) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 o;
+                o.x = __uint_as_float(v[4 * q + 0]); o.y = __uint_as_float(v[4 * q + 1]);
+                o.z = __uint_as_float(v[4 * q + 2]); o.w = __uint_as_float(v[4 * q + 3]);
+                if (a.bias) {
+                    const float4 b = __ldg(reinterpret_cast<const float4 *>(a.bias + c0 + 4 * q));
+                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                }
+                *reinterpret_cast<float4 *>(stage_out + my_row * OUT_LD + c0 + 4 * q) = o;
+            }
+        }
+        tc_fence_before();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (a.stats && tid < BN) {   // training-mode BatchNorm statistics of the pre-affine output
+            float s = 0.f, q = 0.f;
+            const int rows = (int)min((long long)BM, a.m_out - row0);
+            for (int r = 0; r < rows; ++r) { float t = stage_out[r * OUT_LD + tid]; s += t; q += t * t; }
+            atomicAdd(a.stats + tid, s);
+            atomicAdd(a.stats + a.cout + tid, q);
+        }
+        if (BN > NPROD && a.stats && tid + NPROD < BN) {
+            float s = 0.f, q = 0.f;
+            const int rows = (int)min((long long)BM, a.m_out - row0);
+            for (int r = 0; r < rows; ++r) { float t = stage_out[r * OUT_LD + tid + NPROD]; s += t; q += t * t; }
+            atomicAdd(a.stats + tid + NPROD, s);
+            atomicAdd(a.stats + a.cout + tid + NPROD, q);
+        }
+        constexpr int V_PER_ROW = BN / 4;
+        for (int t = tid; t < BM * V_PER_ROW; t += NPROD) {
+            const int r = t / V_PER_ROW, cv = (t % V_PER_ROW) * 4;
+            const long long row = row0 + r;
+            if (row >= a.m_out) break;
+            float4 o = *reinterpret_cast<const float4 *>(stage_out + r * OUT_LD + cv);
+            if (a.scale) {
+                const float4 sc = __ldg(reinterpret_cast<const float4 *>(a.scale + cv));
+                const float4 sh = __ldg(reinterpret_cast<const float4 *>(a.shift + cv));
+                o.x = fmaf(o.x, sc.x, sh.x); o.y = fmaf(o.y, sc.y, sh.y); o.z = fmaf(o.z, sc.z, sh.z); o.w = fmaf(o.w, sc.w, sh.w);
+            }
+            if (a.residual) {
+                const float4 rs = __ldg(reinterpret_cast<const float4 *>(a.residual + row * a.cout + cv));
+                o.x += rs.x; o.y += rs.y; o.z += rs.z; o.w += rs.w;
+            }
+            if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *reinterpret_cast<float4 *>(a.y + row * a.cout + cv) = o;
+        }
+    } else {
+        // ================= MMA issuer (warp 4) =================
+        for (int it = 0; it < n_iters; ++it) {
+            const int s = it % STAGES;
+            mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t st = smem_u32(tiles + s * STAGE);
+                const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + A_BYTES);
+                const uint64_t b_hi = make_desc(st + 2 * A_BYTES), b_lo = make_desc(st + 2 * A_BYTES + B_BYTES);
+                const int kb = it % kblocks;
+                const int k8n = min(BK / 8, (a.cin - kb * BK + 7) / 8);
+                for (int k8 = 0; k8 < k8n; ++k8) {
+                    const uint64_t adv = (uint64_t)((k8 * 32) >> 4);   // +32 bytes along K inside the swizzle row
+                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, IDESC, (it | k8) ? 1u : 0u);
+                    umma_tf32(tmem_base, a_lo + adv, b_hi + adv, IDESC, 1u);
+                    umma_tf32(tmem_base, a_hi + adv, b_lo + adv, IDESC, 1u);
+                }
+                umma_commit(empty0 + 8 * s);            // frees the stage once these MMAs have read it
+                if (it == n_iters - 1) umma_commit(accum_bar);
+            }
+            __syncwarp();
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols(BN)));
+    }
+}
+
+template <int BN>
+size_t smem_bytes(int K) { return 1024 + (size_t)stages_for(BN) * stage_bytes(BN) + (size_t)K * BM * 4 + (2 * stages_for(BN) + 1) * 8 + 16; }
+
+template <int BN>
+int32_t launch_tc(const TcArgs &a, cudaStream_t stream)
+{
+    static bool configured = false;
+    const size_t smem = smem_bytes<BN>(MAX_TAPS);
+    if (!configured) {
+        CPD_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    gather_gemm_tc_kernel<BN><<<(unsigned)div_up(a.m_out, BM), NTHREADS, smem_bytes<BN>(a.K), stream>>>(a);
+    count_launch();
+    return launch_status("cpd_gather_gemm[tcgen05]");
+}
+
+}  // namespace
+
+bool gather_gemm_tc_supported(int32_t cin, int32_t K, int32_t cout)
+{
+    return cin % 8 == 0 && cin >= 8 && K <= MAX_TAPS && (cout == 16 || cout == 32 || cout == 64 || cout == 128 || cout == 256);
+}
+
+size_t gather_gemm_tc_workspace(int64_t, int32_t, int32_t, int32_t) { return 16; }
+
+int32_t gather_gemm_tc(const float *x, int64_t, int32_t cin, const float *w, int32_t K, int32_t cout, const int32_t *nbr,
+                       int64_t m_out, const float *bias, const float *scale, const float *shift, const float *residual,
+                       int32_t relu, float *stats, float *y, void *, size_t, cudaStream_t stream)
+{
+    CPD_REQUIRE(gather_gemm_tc_supported(cin, K, cout), CPD_ERR_UNSUPPORTED, "tcgen05 gather-GEMM: unsupported shape");
+    CPD_REQUIRE((((uintptr_t)x | (uintptr_t)w | (uintptr_t)y | (uintptr_t)bias | (uintptr_t)scale | (uintptr_t)shift |
+                  (uintptr_t)residual) & 15) == 0, CPD_ERR_MISALIGNED, "tcgen05 gather-GEMM: pointers must be 16-byte aligned");
+    TcArgs a{x, w, bias, scale, shift, residual, nbr, stats, y, m_out, cin, K, cout, relu};
+    switch (cout) {
+        case 16: return launch_tc<16>(a, stream);
+        case 32: return launch_tc<32>(a, stream);
+        case 64: return launch_tc<64>(a, stream);
+        case 128: return launch_tc<128>(a, stream);
+        default: return launch_tc<256>(a, stream);
+    }
+}
+
 }  // namespace cpd

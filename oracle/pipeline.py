@@ -49,8 +49,20 @@ def run_sequential(seq, feats, coords, shape, cache):
     return feats, coords, shape
 
 
-def backbone_forward(net, frames, pc_range, voxel_size, max_pts=5, max_voxels=1000000, sfx=""):
-    """frames: list of (n_i, C) numpy clouds -> (features, coords (M,4), shape, stage dict)."""
+def decompose(feats, coords, shape, i=0):
+    """VoxelBackBone8x.decompose_tensor (spconv_backbone.py:241-260): strict `<` on both slab
+    bounds, so x == i*W/4 is dropped -- a reference quirk that is reproduced, not fixed."""
+    w4 = shape[2] // 4
+    keep = (i * w4 < coords[:, 3]) & (coords[:, 3] < (i + 1) * w4)
+    c = coords[keep].copy()
+    c[:, 3] -= i * w4
+    return feats[keep], c, [shape[0], shape[1], w4]
+
+
+def backbone_forward(net, frames, pc_range, voxel_size, max_pts=5, max_voxels=1000000, sfx="", eval_wide=False):
+    """frames: list of (n_i, C) numpy clouds -> (features, coords (M,4), shape, stage dict).
+    eval_wide: VoxelBackBone8x's eval path (spconv_backbone.py:332-393): the tower runs on a
+    [D, H, 4*W] grid and the outputs are cut back with decompose()."""
     feats, coords = [], []
     for b, pts in enumerate(frames):
         v, c, n = O.voxelize(pts, pc_range, voxel_size, max_pts, max_voxels)
@@ -58,10 +70,14 @@ def backbone_forward(net, frames, pc_range, voxel_size, max_pts=5, max_voxels=10
         coords.append(np.concatenate([np.full((len(c), 1), b, np.int32), c], 1))
     feats, coords = np.concatenate(feats, 0), np.concatenate(coords, 0)
     shape, cache, stages = list(net.sparse_shape), {}, {}
+    if eval_wide:
+        shape[2] *= 4
     names = ["conv_input", "conv1", "conv2", "conv3", "conv4"] + (["conv_out"] if sfx == "" else [])
     for name in names:
         feats, coords, shape = run_sequential(getattr(net, name + sfx if name != "conv_out" else name), feats, coords, shape, cache)
         stages[name] = (feats, coords, list(shape))
+    if eval_wide:
+        feats, coords, shape = decompose(feats, coords, shape, 0)
     return feats, coords, shape, stages
 
 

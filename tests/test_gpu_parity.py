@@ -253,7 +253,7 @@ def test_voxel_backbone8x_forward_matches_oracle(oracle, cuda):
         out = net(dict(bd))
     t = out["encoded_spconv_tensor"]
     from oracle import pipeline
-    feats, coords, shape, _ = pipeline.backbone_forward(net, [pts], PC_RANGE, VOXEL_SIZE)
+    feats, coords, shape, _ = pipeline.backbone_forward(net, [pts], PC_RANGE, VOXEL_SIZE, eval_wide=True)
     assert t.spatial_shape == shape == [2, 188, 188]
     assert np.array_equal(t.indices.cpu().numpy(), coords)
     ref_scale = max(1.0, float(np.abs(feats).max()))
