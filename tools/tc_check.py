@@ -25,6 +25,14 @@ for (m_in, m_out, cin, cout, K) in [(300, 128, 32, 64, 27), (5000, 5000, 64, 64,
     t0 = time.time()
     got = ops.gather_gemm(x, w, nbr, bias=bias, scale=scale, shift=shift, residual=res, relu=True, stats=st_b, algo=ops.ALGO_TCGEN05)
     torch.cuda.synchronize()
+    x64, w64 = x.double(), w.double()
+    ex = torch.zeros(m_out, cout, dtype=torch.float64, device=dev)
+    for k in range(K):
+        idx = nbr[:, k].long()
+        ex += torch.where((idx >= 0)[:, None], x64[idx.clamp(min=0)], torch.zeros((), dtype=torch.float64, device=dev)) @ w64[:, k, :].T
+    e_tc = (ops.gather_gemm(x, w, nbr, algo=ops.ALGO_TCGEN05).double() - ex).abs().max().item()
+    e_simt = (ops.gather_gemm(x, w, nbr, algo=ops.ALGO_SIMT).double() - ex).abs().max().item()
+    print(f"   vs fp64: tc {e_tc:.2e}  simt {e_simt:.2e}  (|y|max {ex.abs().max().item():.2f})", flush=True)
     err = (got - ref).abs().max().item()
     serr = ((st_a - st_b).abs() / (st_a.abs() + 1)).max().item()
     plain = (ops.gather_gemm(x, w, nbr, algo=ops.ALGO_TCGEN05) - ops.gather_gemm(x, w, nbr, algo=ops.ALGO_SIMT)).abs().max().item()
@@ -38,7 +46,7 @@ for (m_in, m_out, cin, cout, K) in [(300, 128, 32, 64, 27), (5000, 5000, 64, 64,
         ms = e0.elapsed_time(e1) / 5
         P = int((nbr >= 0).sum())
         print(f"   {name}: {ms*1e3:8.1f} us  {2.0*P*cin*cout/ms/1e9:7.1f} TFLOP/s (useful)", flush=True)
-    good = err < 1e-4 and plain < 1e-4 and serr < 1e-3
+    good = e_tc < 1e-4 and err < 2e-4 and serr < 1e-3
     ok &= good
     print(f"m_out={m_out} cin={cin} cout={cout} K={K}: max|tc-simt| fused={err:.2e} plain={plain:.2e} stats={serr:.2e} {'OK' if good else 'FAIL'}", flush=True)
 print("ALL OK" if ok else "SOME FAILED")
