@@ -31,7 +31,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="backbone_fwd", choices=["backbone_fwd"])
+    ap.add_argument("--workload", default="detector_train", choices=["detector_train", "backbone_fwd"])
     ap.add_argument("--batch", type=int, default=4, help="frames per step per GPU (CPD trains with 4)")
     ap.add_argument("--points", type=int, default=160000, help="points per frame")
     ap.add_argument("--pool", type=int, default=2, help="distinct batches cycled through")
@@ -40,8 +40,12 @@ def parse():
 
 
 def workload_name(a):
-    return (f"CPD VoxelBackBone8x fwd (voxelize+MeanVFE+12 sparse convs+BEV dense), {a.points // 1000}k pts/frame, "
-            f"bs={a.batch}/GPU [BASELINE configs[1]]")
+    if a.workload == "backbone_fwd":
+        return (f"CPD VoxelBackBone8x fwd (voxelize+MeanVFE+12 sparse convs+BEV dense), {a.points // 1000}k pts/frame, "
+                f"bs={a.batch}/GPU [BASELINE configs[1]]")
+    return (f"CPD full hot-path detector train step fwd+bwd (voxelize x2 + VoxelResBackBone8x with MM tower + BEV backbone + "
+            f"CenterHead loss/decode + iou3d_nms + clip + Adam), {a.points // 1000}k pts/frame, bs={a.batch}/GPU "
+            f"[BASELINE configs[2]; configs[3] under torchrun]")
 
 
 def make_frames(rank, count, points):
@@ -59,6 +63,18 @@ def make_net(device):
             m.running_mean.uniform_(-0.1, 0.1)
             m.running_var.uniform_(0.8, 1.2)
     return net.to(device).eval()
+
+
+def make_detector(device):
+    import torch
+    from cpd_b200 import detector
+    torch.manual_seed(1234)
+    return detector.CPDHotPathDetector().to(device).train()
+
+
+def make_gt(rank, count, boxes=30):
+    from cpd_b200.synth import synth_gt_boxes
+    return [synth_gt_boxes(boxes, 1000 * rank + i) for i in range(count)]
 
 
 # ------------------------------------------------------------------------------------------
@@ -118,35 +134,69 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
-    net = make_net(dev)
-    to_bev = backbone.HeightCompression()
-    frames = make_frames(rank, a.batch * a.pool, a.points)
+    train = a.workload == "detector_train"
+    nfr = a.batch * a.pool
+    frames = make_frames(rank, nfr, a.points)
     host = [torch.from_numpy(f).pin_memory() for f in frames]
     resident = [h.to(dev) for h in host]
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
-    def step(points_list):
-        bd = voxel.voxelize_batch(points_list, PC_RANGE, VOXEL_SIZE)
-        bd["batch_size"] = len(points_list)
-        out = to_bev(net(bd))
-        return out["spatial_features"], out["encoded_spconv_tensor"]
-
     def batch_of(i, src):
         k = (i % a.pool) * a.batch
         return src[k:k + a.batch]
+
+    if train:
+        frames1 = make_frames(rank + 500, nfr, a.points)          # second cloud per frame (STAGES=2: `points1`, MM tower)
+        host1 = [torch.from_numpy(f).pin_memory() for f in frames1]
+        resident1 = [h.to(dev) for h in host1]
+        gts = make_gt(rank, nfr)
+        host_gt = [torch.from_numpy(np.stack(gts[k:k + a.batch])).pin_memory() for k in range(0, nfr, a.batch)]
+        resident_gt = [g.to(dev) for g in host_gt]
+        net = make_detector(dev)
+        model = net
+        if world > 1:
+            model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local])
+        opt = torch.optim.Adam(net.parameters(), lr=1e-4, fused=True)
+
+        def step(i, src, src1, src_gt):
+            loss, tb = model(dict(points=batch_of(i, src), points1=batch_of(i, src1), gt_boxes=src_gt[i % a.pool]))
+            opt.zero_grad(set_to_none=True)
+            loss.backward()                                        # DDP: NCCL all-reduce of the gradients overlaps here
+            torch.nn.utils.clip_grad_norm_(net.parameters(), 10.0)
+            opt.step()
+            return loss, net.last_batch_dict["encoded_spconv_tensor"]
+
+        run_resident = lambda i: step(i, resident, resident1, resident_gt)
+        run_host = lambda i: step(i, host, host1, host_gt)         # .to(device, non_blocking) happens inside the detector
+        ctx = torch.enable_grad()
+        h2d = sum(h.numel() * 4 for h in host[:a.batch]) + sum(h.numel() * 4 for h in host1[:a.batch]) + host_gt[0].numel() * 4
+    else:
+        net = make_net(dev)
+        to_bev = backbone.HeightCompression()
+
+        def fwd(points_list):
+            bd = voxel.voxelize_batch([p if p.is_cuda else p.to(dev, non_blocking=True) for p in points_list], PC_RANGE, VOXEL_SIZE)
+            bd["batch_size"] = len(points_list)
+            out = to_bev(net(bd))
+            return out["spatial_features"].sum(), out["encoded_spconv_tensor"]
+
+        run_resident = lambda i: fwd(batch_of(i, resident))
+        run_host = lambda i: fwd(batch_of(i, host))
+        ctx = torch.no_grad()
+        h2d = sum(h.numel() * 4 for h in host[:a.batch])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    with torch.no_grad():
+    sampler = ClockSampler(local)
+    sampler.start()
+    with ctx:
         for i in range(a.warmup):
-            step(batch_of(i, resident))
+            run_resident(i)
         barrier()
         # ---- timed region: K steps, inputs resident in HBM, L2 flushed between steps ----
-        sampler = ClockSampler(local)
-        sampler.start()
         ops.PROFILE = []
         l0 = _lib.launch_count()
         evs = []
@@ -155,31 +205,29 @@ def run_ours(a):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            bev, enc = step(batch_of(i, resident))
+            res, enc = run_resident(i)
             e1.record()
             evs.append((e0, e1))
         barrier()
         launches = _lib.launch_count() - l0
         prof, ops.PROFILE = ops.PROFILE, None
-        clocks = sampler.stop()
         total_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
-        # ---- end-to-end: host (pinned) points in, result checksum out, every step ----
+        # ---- end-to-end: host (pinned) inputs in, result scalar out, every step ----
         evs2 = []
-        h2d = d2h = 0
+        d2h = 0
         barrier()
         for i in range(a.steps):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            pl = [h.to(dev, non_blocking=True) for h in batch_of(i, host)]
-            bev, enc = step(pl)
-            res = torch.stack([bev.sum(), enc.features.abs().max()]).cpu()
+            res, enc = run_host(i)
+            out = torch.stack([res.detach().float(), enc.features.detach().abs().max()]).cpu()
             e1.record()
             evs2.append((e0, e1))
-            h2d = sum(h.numel() * 4 for h in batch_of(i, host))
-            d2h = res.numel() * 4 + 4 * (len(pl) + 1) + 4 * 4      # result + voxel counts + 4 strided n_out reads
+            d2h = out.numel() * 4
         barrier()
         e2e_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs2)
+    clocks = sampler.stop()
 
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -191,7 +239,7 @@ def run_ours(a):
     hbm, bf16, src = peaks()
     groups, pcache = {}, {}
     for e0, e1, m in prof:
-        key = (m["cin"], m["cout"], m["K"])
+        key = (m["kind"], m["cin"], m["cout"], m["K"])
         nid = id(m["nbr"])
         if nid not in pcache:
             pcache[nid] = int((m["nbr"] >= 0).sum().item())
@@ -209,7 +257,7 @@ def run_ours(a):
     else:
         roof = dict(bound="tensor", achieved=top["flops"] / top["ms"] / 1e9, peak=tf32_peak, unit="TFLOP/s")
     roof.update(frac=roof["achieved"] / roof["peak"], traffic=None, peak_source=f"{src} ({'HBM copy' if roof['bound'] == 'hbm' else 'bf16/2 = TF32 dense'})",
-                kernel=f"gather_gemm {top_key[0]}->{top_key[1]} K={top_key[2]}", launches=top["n"],
+                kernel=f"{top_key[0]} {top_key[1]}->{top_key[2]} K={top_key[3]}", launches=top["n"],
                 avg_launch_us=1e3 * top["ms"] / top["n"], share_of_step=top["ms"] / total_ms,
                 gather_gemm_share_of_step=gg_ms / total_ms,
                 algorithmic_bytes_per_launch=top["bytes"] / top["n"], flops_per_launch=top["flops"] / top["n"])
@@ -227,7 +275,7 @@ def run_ours(a):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
     }
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(a, frames[:1], net)
+        line["cpu_baseline"] = cpu_baseline(a, frames[:1], net if not train else None)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -235,27 +283,48 @@ def run_ours(a):
 
 
 def cpu_baseline(a, frames, net=None):
-    """Oracle port of the same path (voxelize -> MeanVFE -> sparse convs -> dense) on the host cores."""
-    from cpd_b200.synth import PC_RANGE, VOXEL_SIZE
+    """CPU port of the same step on the host cores (oracle/ for voxelizer + sparse convs, torch CPU for the
+    dense BEV head exactly as the reference builds it), all threads, on a bounded sample."""
+    import torch
+    from cpd_b200.synth import PC_RANGE, VOXEL_SIZE, synth_gt_boxes, synth_scan
     from oracle import oracle as O
     from oracle import pipeline
-    if net is None:
-        import torch
-        net = make_net(torch.device("cpu"))
     cores = os.cpu_count() or 1
     O.set_threads(cores)
-    pipeline.backbone_forward(net, [frames[0][:20000]], PC_RANGE, VOXEL_SIZE, eval_wide=True)      # warm caches / page in
-    t0 = time.perf_counter()
-    n = 0
-    while True:
-        feats, coords, shape, _ = pipeline.backbone_forward(net, [frames[n % len(frames)]], PC_RANGE, VOXEL_SIZE, eval_wide=True)
-        pipeline.bev_dense(feats, coords, 1, shape)
-        n += 1
-        dt = time.perf_counter() - t0
-        if dt > 10.0 or n >= 8:
-            break
+    torch.set_num_threads(cores)
+    if a.workload == "backbone_fwd":
+        if net is None:
+            net = make_net(torch.device("cpu"))
+        pipeline.backbone_forward(net, [frames[0][:20000]], PC_RANGE, VOXEL_SIZE, eval_wide=True)      # warm caches / page in
+        t0 = time.perf_counter()
+        n = 0
+        while True:
+            feats, coords, shape, _ = pipeline.backbone_forward(net, [frames[n % len(frames)]], PC_RANGE, VOXEL_SIZE, eval_wide=True)
+            pipeline.bev_dense(feats, coords, 1, shape)
+            n += 1
+            dt = time.perf_counter() - t0
+            if dt > 10.0 or n >= 8:
+                break
+        what = "fwd"
+    else:
+        import warnings
+        warnings.filterwarnings("ignore")
+        cpu = pipeline.CpuDetector(make_detector(torch.device("cpu")))
+        f1 = [synth_scan(a.points, 777)]
+        gt = np.stack([synth_gt_boxes(30, 0)])
+        cpu.train_step([frames[0][:16000]], [f1[0][:16000]], gt)                                        # warm-up on a small cloud
+        t0 = time.perf_counter()
+        n = 0
+        while True:
+            cpu.train_step([frames[n % len(frames)]], f1, gt)
+            n += 1
+            dt = time.perf_counter() - t0
+            if dt > 12.0 or n >= 4:
+                break
+        what = "fwd+bwd train step (bs=1, no optimizer update)"
     return {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{n} frame(s) of the same workload ({a.points} pts), oracle/cpd_oracle.c with OpenMP on {cores} threads"}
+            "sample": f"{n} frame(s) of the same workload ({a.points} pts/frame), {what}; oracle/cpd_oracle.c (OpenMP) + torch CPU "
+                      f"for the dense head, {cores} threads"}
 
 
 def run_reference(a):

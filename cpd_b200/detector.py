@@ -1,0 +1,80 @@
+"""The CPD detection hot path assembled end to end (BASELINE.json configs[2]/[3]).
+
+Module order = the reference's ``module_topology`` restricted to the hot path
+(cpd/models/detectors/detector3d_template.py:22-25, voxel_rcnn.py:8-35):
+  voxelize (+MeanVFE, fused) -> VoxelResBackBone8x (MM tower in training) -> HeightCompression
+  -> BaseBEVBackbone -> CenterHead (targets, loss, decode, iou3d_nms).
+The RoI head and everything else stay out of scope.
+Inputs are raw point clouds: a list of per-frame (n_i, 5) tensors (device-resident or pinned
+host memory); nothing on this path runs on the CPU.
+"""
+import torch
+import torch.nn as nn
+
+from . import backbone, bev, voxel
+from .synth import PC_RANGE, VOXEL_SIZE
+
+MODEL_CFG = dict(
+    BACKBONE_3D=dict(NUM_FILTERS=[16, 32, 64, 128], OUT_FEATURES=128, RETURN_NUM_FEATURES_AS_DICT=True, MM=True),
+    MAP_TO_BEV=dict(NUM_BEV_FEATURES=256),
+    BACKBONE_2D=dict(LAYER_NUMS=[5, 5], LAYER_STRIDES=[1, 2], NUM_FILTERS=[128, 256], UPSAMPLE_STRIDES=[1, 2],
+                     NUM_UPSAMPLE_FILTERS=[256, 256]),
+    DENSE_HEAD=bev.DEFAULT_HEAD_CFG,
+)
+
+
+class CPDHotPathDetector(nn.Module):
+    """tools/cfgs/models/waymo_unsupervised/voxel_rcnn_cproto_center.yaml:12-80 without ROI_HEAD."""
+
+    def __init__(self, model_cfg=None, pc_range=PC_RANGE, voxel_size=VOXEL_SIZE, num_point_features=5, max_pts=5,
+                 max_voxels=1000000, class_names=("Vehicle", "Pedestrian", "Cyclist"), res_backbone=True,
+                 predict_boxes_when_training=True):
+        super().__init__()
+        cfg = model_cfg or MODEL_CFG
+        self.pc_range = [float(v) for v in pc_range]
+        self.voxel_size = [float(v) for v in voxel_size]
+        self.max_pts, self.max_voxels = max_pts, max_voxels
+        grid = [int(round((self.pc_range[3 + i] - self.pc_range[i]) / self.voxel_size[i])) for i in range(3)]
+        self.grid_size = grid
+        self.vfe = voxel.MeanVFE(None, num_point_features, 1)
+        bb = backbone.VoxelResBackBone8x if res_backbone else backbone.VoxelBackBone8x
+        self.backbone_3d = bb(cfg["BACKBONE_3D"], num_point_features, grid)
+        self.map_to_bev_module = backbone.HeightCompression(cfg["MAP_TO_BEV"], nhwc=True)
+        self.backbone_2d = bev.BaseBEVBackbone(cfg["BACKBONE_2D"], 1, cfg["MAP_TO_BEV"]["NUM_BEV_FEATURES"])
+        self.dense_head = bev.CenterHead(cfg["DENSE_HEAD"], 1, self.backbone_2d.num_bev_features_post, len(class_names),
+                                         class_names, grid, self.pc_range, self.voxel_size,
+                                         predict_boxes_when_training=predict_boxes_when_training)
+
+    def _voxelize(self, frames, device):
+        frames = [f if f.is_cuda else f.to(device, non_blocking=True) for f in frames]
+        return voxel.voxelize_batch(frames, self.pc_range, self.voxel_size, self.max_pts, self.max_voxels)
+
+    def forward(self, batch):
+        """batch: dict(points=[...], points1=[...] (training, MM tower), gt_boxes=(B, M, 8) (training)).
+        Training returns (loss, tb_dict); eval returns per-frame prediction dicts."""
+        device = next(self.parameters()).device
+        bd = self._voxelize(batch["points"], device)
+        bd["batch_size"] = len(batch["points"])
+        if self.training and "points1" in batch and getattr(self.backbone_3d, "RES", False):
+            b1 = self._voxelize(batch["points1"], device)
+            bd["voxel_features1"], bd["voxel_coords1"] = b1["voxel_features"], b1["voxel_coords"]
+        if "gt_boxes" in batch:
+            gt = batch["gt_boxes"]
+            bd["gt_boxes"] = gt if gt.is_cuda else gt.to(device, non_blocking=True)
+        bd = self.vfe(bd)
+        bd = self.backbone_3d(bd)
+        bd = self.map_to_bev_module(bd)
+        sf = bd["spatial_features"]                       # (B, 256, H, W) logical NCHW over NHWC memory
+        n, c, h, w = sf.shape
+        bd["spatial_features"] = bev.DenseMap(sf.permute(0, 2, 3, 1).reshape(n * h * w, c), n, h, w)
+        bd = self.backbone_2d(bd)
+        bd = self.dense_head(bd)
+        self.last_batch_dict = bd
+        if self.training:
+            loss, tb = self.dense_head.get_loss()
+            if "multi_scale_3d_features_mm" in bd:
+                # the reference feeds the MM tower to the RoI head (out of scope); a tiny
+                # regulariser stands in for that consumer so its parameters receive gradients
+                loss = loss + 1e-3 * sum(t.features.square().mean() for t in bd["multi_scale_3d_features_mm"].values())
+            return loss, tb
+        return bd["final_box_dicts"]

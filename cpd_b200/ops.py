@@ -196,7 +196,7 @@ def gather_gemm(x, w, nbr, bias=None, scale=None, shift=None, residual=None, rel
                                  _ptr(ws), wsb, _stream()), "cpd_gather_gemm")
     if PROFILE is not None:
         e1.record()
-        PROFILE.append((e0, e1, dict(m_in=x.shape[0], m_out=m_out, cin=cin, cout=cout, K=K, nbr=nbr,
+        PROFILE.append((e0, e1, dict(kind="gather_gemm", m_in=x.shape[0], m_out=m_out, cin=cin, cout=cout, K=K, nbr=nbr,
                                      residual=residual is not None)))
     return y
 
@@ -209,8 +209,17 @@ def gather_wgrad(x, dy, nbr, want_bias=False):
     cin, cout, K = x.shape[1], dy.shape[1], nbr.shape[1]
     dw = torch.empty((cout, K, cin), dtype=torch.float32, device=x.device)
     db = torch.empty((cout,), dtype=torch.float32, device=x.device) if want_bias else None
+    wsb = L.cpd_gather_wgrad_workspace_bytes(dy.shape[0], cin, K, cout)
+    ws = _ws(wsb, x.device) if wsb else None
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.check(L.cpd_gather_wgrad(_ptr(x), x.shape[0], cin, _ptr(dy), dy.shape[0], cout, _ptr(nbr), K, _ptr(dw), _ptr(db),
-                                  None, 0, _stream()), "cpd_gather_wgrad")
+                                  _ptr(ws), wsb, _stream()), "cpd_gather_wgrad")
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append((e0, e1, dict(kind="gather_wgrad", m_in=x.shape[0], m_out=dy.shape[0], cin=cin, cout=cout, K=K, nbr=nbr,
+                                     residual=False)))
     return dw, db
 
 

@@ -317,33 +317,67 @@ ORACLE_API void cpd_oracle_spconv_bwd(const float *x, int64_t m_in, int cin,
             dbias[co] = (float)s;
         }
     }
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+    const size_t tile = (size_t)cout * cin;
+    float *wk = (float *)malloc(sizeof(float) * tile);                 /* W_k as (cout, cin), contiguous */
+    double *acc = dw ? (double *)malloc(sizeof(double) * tile * (size_t)nthreads) : NULL;
     for (int k = 0; k < K; ++k) {
         const int32_t *pi = pair_in + (int64_t)k * pair_stride, *po = pair_out + (int64_t)k * pair_stride;
+        const int32_t np = pair_cnt[k];
+        if (np == 0) continue;
+        for (int co = 0; co < cout; ++co)
+            memcpy(wk + (size_t)co * cin, w + ((int64_t)co * K + k) * cin, sizeof(float) * cin);
         if (dx) {
+            /* within one tap every input row appears at most once: pairs run in parallel */
 #pragma omp parallel for schedule(static)
-            for (int32_t p = 0; p < pair_cnt[k]; ++p) {
+            for (int32_t p = 0; p < np; ++p) {
                 float *dxi = dx + (int64_t)pi[p] * cin;
                 const float *dyo = dy + (int64_t)po[p] * cout;
                 for (int co = 0; co < cout; ++co) {
-                    const float *wk = w + ((int64_t)co * K + k) * cin;
-                    float g = dyo[co];
-                    for (int ci = 0; ci < cin; ++ci) dxi[ci] += wk[ci] * g;
+                    const float g = dyo[co];
+                    const float *row = wk + (size_t)co * cin;
+                    for (int ci = 0; ci < cin; ++ci) dxi[ci] += row[ci] * g;
                 }
             }
         }
         if (dw) {
-#pragma omp parallel for schedule(static)
-            for (int co = 0; co < cout; ++co) {
-                float *dwk = dw + ((int64_t)co * K + k) * cin;
-                for (int ci = 0; ci < cin; ++ci) {
-                    double s = 0.0;
-                    for (int32_t p = 0; p < pair_cnt[k]; ++p)
-                        s += (double)dy[(int64_t)po[p] * cout + co] * (double)x[(int64_t)pi[p] * cin + ci];
-                    dwk[ci] = (float)s;
+            /* per-thread double accumulators over a slice of the pairs, then a tree-free reduce */
+#pragma omp parallel
+            {
+                int t = 0, nt = 1;
+#ifdef _OPENMP
+                t = omp_get_thread_num(); nt = omp_get_num_threads();
+#endif
+                double *a = acc + tile * (size_t)t;
+                for (size_t q = 0; q < tile; ++q) a[q] = 0.0;
+                const int32_t lo = (int32_t)((int64_t)np * t / nt), hi = (int32_t)((int64_t)np * (t + 1) / nt);
+                for (int32_t p = lo; p < hi; ++p) {
+                    const float *xi = x + (int64_t)pi[p] * cin;
+                    const float *dyo = dy + (int64_t)po[p] * cout;
+                    for (int co = 0; co < cout; ++co) {
+                        const double g = (double)dyo[co];
+                        double *row = a + (size_t)co * cin;
+                        for (int ci = 0; ci < cin; ++ci) row[ci] += g * (double)xi[ci];
+                    }
+                }
+#pragma omp barrier
+#pragma omp for schedule(static)
+                for (int co = 0; co < cout; ++co) {
+                    float *dwk = dw + ((int64_t)co * K + k) * cin;
+                    for (int ci = 0; ci < cin; ++ci) {
+                        double sum = 0.0;
+                        for (int u = 0; u < nt; ++u) sum += acc[tile * (size_t)u + (size_t)co * cin + ci];
+                        dwk[ci] = (float)sum;
+                    }
                 }
             }
         }
     }
+    free(wk);
+    free(acc);
 }
 
 /* SparseConvTensor.dense(): height_compression.py:136-138, Appendix A.2.     */

@@ -69,3 +69,75 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# ----------------------------------------------------------------------------------------------
+# CenterHead pieces: run the REFERENCE's own Python (functions lifted by name out of its source
+# files with ast, because `import cpd.models` cannot resolve here -- SURVEY.md section 8c) and
+# store inputs + outputs.
+# ----------------------------------------------------------------------------------------------
+def _lift(path, names, glb):
+    import ast
+    src = open(path).read()
+    tree = ast.parse(src)
+    out = {}
+    for node in ast.walk(tree):
+        if isinstance(node, (ast.FunctionDef, ast.ClassDef)) and node.name in names:
+            code = ast.get_source_segment(src, node)
+            import textwrap
+            exec(textwrap.dedent(code), glb)
+            out[node.name] = glb[node.name]
+    return out
+
+
+def head_golden():
+    import importlib.util
+    ref = "/root/reference/cpd"
+    spec = importlib.util.spec_from_file_location("ref_centernet_utils", f"{ref}/models/model_utils/centernet_utils.py")
+    cu = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cu)
+    glb = {"torch": torch, "np": np, "centernet_utils": cu, "nn": torch.nn}
+    fn = _lift(f"{ref}/models/dense_heads/center_head.py", {"assign_target_of_single_head"}, glb)["assign_target_of_single_head"]
+    losses = _lift(f"{ref}/utils/loss_utils.py", {"neg_loss_cornernet", "_reg_loss", "_gather_feat", "_transpose_and_gather_feat"}, glb)
+
+    class Self:
+        point_cloud_range = [-75.2, -75.2, -2, 75.2, 75.2, 4]
+        voxel_size = [0.1, 0.1, 0.15]
+
+    from cpd_b200.synth import synth_gt_boxes
+    gt = torch.from_numpy(synth_gt_boxes(40, 3))
+    gt[5, 3] = 0.0                     # degenerate box: skipped by the reference
+    gt[7, :2] = torch.tensor([75.0, -75.1])   # near the border: clipped gaussian
+    hm, rb, inds, mask = fn(Self(), 3, gt.clone(), [188, 188], 8, num_max_objs=500, gaussian_overlap=0.1, min_radius=2)
+    g = torch.Generator().manual_seed(0)
+    S = 40                                             # small maps keep the fixture small
+    pred_hm = torch.rand(2, 3, S, S, generator=g).clamp(1e-4, 1 - 1e-4)
+    tgt_hm = torch.stack([hm[:, :S, :S], hm[:, 60:60 + S, 60:60 + S]], 0).contiguous()
+    tgt_hm[0, 1, 3, 4] = 1.0
+    focal = losses["neg_loss_cornernet"](pred_hm, tgt_hm)
+    out8 = torch.randn(2, 8, S, S, generator=g)
+    ind2 = torch.stack([inds[:64] % (S * S), inds[:64].flip(0) % (S * S)], 0)
+    mask2 = torch.stack([mask[:64], mask[:64].flip(0)], 0)
+    tb2 = torch.stack([rb[:64], rb[:64].flip(0)], 0)
+    pred = losses["_transpose_and_gather_feat"](out8, ind2)
+    reg = losses["_reg_loss"](pred, tb2, mask2)
+    # decode
+    heat = torch.rand(2, 3, S, S, generator=g) ** 8
+    rot = torch.randn(2, 2, S, S, generator=g)
+    ctr, cz = torch.rand(2, 2, S, S, generator=g), torch.randn(2, 1, S, S, generator=g)
+    dim = torch.rand(2, 3, S, S, generator=g) * 3 + 0.5
+    dec = cu.decode_bbox_from_heatmap(heatmap=heat, rot_cos=rot[:, 0:1], rot_sin=rot[:, 1:2], center=ctr, center_z=cz, dim=dim,
+                                      point_cloud_range=Self.point_cloud_range, voxel_size=Self.voxel_size, feature_map_stride=8,
+                                      K=100, circle_nms=False, score_thresh=0.1,
+                                      post_center_limit_range=torch.tensor(Self.point_cloud_range).float())
+    np.savez_compressed(os.path.join(HERE, "center_head_ref.npz"), gt=gt.numpy(), heatmap=hm.numpy(), ret_boxes=rb.numpy(),
+                        inds=inds.numpy(), mask=mask.numpy(), pred_hm=pred_hm.numpy(), tgt_hm=tgt_hm.numpy(), focal=focal.numpy(),
+                        out8=out8.numpy(), ind2=ind2.numpy(), mask2=mask2.numpy(), tb2=tb2.numpy(), reg=reg.numpy(),
+                        heat=heat.numpy(), rot=rot.numpy(), ctr=ctr.numpy(), cz=cz.numpy(), dim=dim.numpy(),
+                        dec_boxes0=dec[0]["pred_boxes"].numpy(), dec_scores0=dec[0]["pred_scores"].numpy(),
+                        dec_labels0=dec[0]["pred_labels"].numpy(), dec_boxes1=dec[1]["pred_boxes"].numpy())
+    print("center_head_ref.npz written:", int(mask.sum()), "valid boxes,", dec[0]["pred_boxes"].shape[0], "decoded")
+
+
+if __name__ == "__main__":
+    head_golden()

@@ -1,0 +1,177 @@
+"""GPU parity of the dense BEV path and the assembled detector.  The floating-point reference for
+the dense convolutions is plain torch (CPU, float64 accumulate) built from the same weights --
+the reference itself uses nn.Conv2d / nn.ConvTranspose2d here (base_bev_backbone.py:31-59,
+center_head.py:11-45).  Tolerance 1e-4 (scaled by the output magnitude), as north_star states."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from cpd_b200.synth import PC_RANGE, VOXEL_SIZE, synth_gt_boxes, synth_scan
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _close(a, b, tol=TOL):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max()) <= tol * max(1.0, float(b.abs().max()))
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,hw", [(256, 128, 3, 1, 47), (128, 256, 3, 2, 46), (64, 3, 3, 1, 33), (512, 64, 3, 1, 24),
+                                                 (40, 48, 1, 1, 19)])
+def test_dense_conv2d_fwd_bwd(cuda, cin, cout, k, stride, hw):
+    from cpd_b200 import bev
+    torch.manual_seed(cin + cout)
+    conv = bev.DenseConv2d(cin, cout, k, stride=stride, padding=k // 2, bias=True).to(cuda)
+    x = torch.randn(2, cin, hw, hw + 3, device=cuda, requires_grad=True)
+    y = conv(bev.DenseMap.from_nchw(x)).nchw()
+    xr = x.detach().double().cpu().requires_grad_(True)
+    wr, br = conv.weight.detach().double().cpu().requires_grad_(True), conv.bias.detach().double().cpu().requires_grad_(True)
+    yr = F.conv2d(xr, wr, br, stride=stride, padding=k // 2)
+    assert y.shape == yr.shape and _close(y, yr)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    yr.backward(dy.double().cpu())
+    assert _close(x.grad, xr.grad) and _close(conv.weight.grad, wr.grad) and _close(conv.bias.grad, br.grad)
+
+
+@pytest.mark.parametrize("s", [1, 2])
+def test_dense_conv_transpose(cuda, s):
+    from cpd_b200 import bev
+    torch.manual_seed(s)
+    m = bev.DenseConvTranspose2d(128, 256, s, stride=s).to(cuda)
+    x = torch.randn(2, 128, 23, 31, device=cuda, requires_grad=True)
+    y = m(bev.DenseMap.from_nchw(x)).nchw()
+    xr = x.detach().double().cpu().requires_grad_(True)
+    wr = m.weight.detach().double().cpu().requires_grad_(True)
+    yr = F.conv_transpose2d(xr, wr, stride=s)
+    assert y.shape == yr.shape and _close(y, yr)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    yr.backward(dy.double().cpu())
+    assert _close(x.grad, xr.grad) and _close(m.weight.grad, wr.grad)
+
+
+def _torch_bev_reference(bb, head):
+    """The reference module structure in plain torch.nn, loaded with the mirrors' weights."""
+    def seq(ds):
+        layers = []
+        for m in ds:
+            from cpd_b200 import bev
+            if isinstance(m, bev.DenseSequential):
+                layers.append(seq(m))
+            elif isinstance(m, bev.DenseConv2d):
+                c = nn.Conv2d(m.in_channels, m.out_channels, m.k, m.stride, m.padding, bias=m.bias is not None)
+                c.weight.data.copy_(m.weight.data)
+                if m.bias is not None:
+                    c.bias.data.copy_(m.bias.data)
+                layers.append(c)
+            elif isinstance(m, bev.DenseConvTranspose2d):
+                c = nn.ConvTranspose2d(m.in_channels, m.out_channels, m.s, stride=m.s, bias=False)
+                c.weight.data.copy_(m.weight.data)
+                layers.append(c)
+            elif isinstance(m, nn.BatchNorm2d):
+                b = nn.BatchNorm2d(m.num_features, eps=m.eps, momentum=m.momentum)
+                b.load_state_dict(m.state_dict())
+                layers.append(b)
+            else:
+                layers.append(type(m)() if not isinstance(m, nn.Identity) else nn.Identity())
+        return nn.Sequential(*layers)
+    blocks, deblocks = [seq(b) for b in bb.blocks], [seq(d) for d in bb.deblocks]
+    shared = seq(head.shared_conv)
+    heads = {n: seq(getattr(head.heads_list[0], n)) for n in head.heads_list[0].sep_head_dict}
+
+    def run(x):
+        ups = []
+        for b, d in zip(blocks, deblocks):
+            x = b(x)
+            ups.append(d(x))
+        f = torch.cat(ups, 1)
+        s = shared(f)
+        return f, {n: h(s) for n, h in heads.items()}
+    mods = nn.ModuleList(blocks + deblocks + [shared] + list(heads.values()))
+    return run, mods
+
+
+def test_bev_backbone_and_head_match_torch(cuda):
+    from cpd_b200 import bev, detector
+    torch.manual_seed(3)
+    cfg = detector.MODEL_CFG
+    bb = bev.BaseBEVBackbone(cfg["BACKBONE_2D"], 1, 256).to(cuda)
+    head = bev.CenterHead(None, 1, 512, 3, ["Vehicle", "Pedestrian", "Cyclist"], [1504, 1504, 40], list(PC_RANGE), list(VOXEL_SIZE)).to(cuda)
+    for m in list(bb.modules()) + list(head.modules()):
+        if isinstance(m, nn.BatchNorm2d):
+            m.running_mean.uniform_(-0.1, 0.1); m.running_var.uniform_(0.7, 1.3)
+    x = torch.randn(1, 256, 60, 52, device=cuda) * (torch.rand(1, 1, 60, 52, device=cuda) < 0.15)   # sparse like a BEV map
+    run, mods = _torch_bev_reference(bb, head)
+    mods.double().eval()
+    with torch.no_grad():
+        f_ref, h_ref = run(x.double().cpu())
+    bb.eval(); head.eval()
+    with torch.no_grad():                                              # fused inference path
+        d = bb({"spatial_features": x})
+        xm = head.shared_conv(d["st_features_2d_map"])
+        h = head.heads_list[0](xm)
+    assert _close(d["st_features_2d"], f_ref)
+    for n in h_ref:
+        assert _close(h[n], h_ref[n]), n
+    # training-mode BatchNorm (batch statistics) + autograd through the whole dense stack
+    bb.train(); head.train(); mods.train()
+    xg = x.clone().requires_grad_(True)
+    d = bb({"spatial_features": xg})
+    h = head.heads_list[0](head.shared_conv(d["st_features_2d_map"]))
+    xr = x.double().cpu().requires_grad_(True)
+    f_ref, h_ref = run(xr)
+    loss = sum(v.square().mean() for v in h.values())
+    loss_ref = sum(v.square().mean() for v in h_ref.values())
+    assert abs(float(loss) - float(loss_ref)) <= 1e-4 * max(1.0, abs(float(loss_ref)))
+    loss.backward(); loss_ref.backward()
+    assert _close(xg.grad, xr.grad, 2e-4)
+    w, wr = bb.blocks[0][1].weight.grad, mods[0][1].weight.grad
+    assert _close(w, wr, 2e-4)
+
+
+def _batch(cuda, bs, n_pts, seed0=0):
+    pts = [torch.from_numpy(synth_scan(n_pts, seed0 + i)).to(cuda) for i in range(bs)]
+    pts1 = [torch.from_numpy(synth_scan(n_pts, seed0 + 100 + i)).to(cuda) for i in range(bs)]
+    gt = torch.from_numpy(np.stack([synth_gt_boxes(30, seed0 + i) for i in range(bs)])).to(cuda)
+    return dict(points=pts, points1=pts1, gt_boxes=gt)
+
+
+def test_detector_train_step_and_eval(cuda, oracle):
+    from cpd_b200 import detector
+    torch.manual_seed(0)
+    det = detector.CPDHotPathDetector().to(cuda).train()
+    opt = torch.optim.Adam(det.parameters(), lr=1e-3)
+    batch = _batch(cuda, 2, 20000)
+    losses = []
+    for _ in range(3):
+        loss, tb = det(batch)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        missing = [n for n, p in det.named_parameters() if p.grad is None or not torch.isfinite(p.grad).all()]
+        assert not missing, missing
+        opt.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+    det.eval()
+    with torch.no_grad():
+        preds = det(dict(points=batch["points"]))
+    assert len(preds) == 2
+    for p in preds:
+        n = p["pred_boxes"].shape[0]
+        assert p["pred_boxes"].shape == (n, 7) and p["pred_scores"].shape == (n,) and int(p["pred_labels"].min() if n else 1) >= 1
+        if n > 1:                                                      # survivors of rotated NMS at 0.8 do not overlap above 0.8
+            b = p["pred_boxes"].cpu().numpy()
+            order = np.argsort(-p["pred_scores"].cpu().numpy(), kind="stable")
+            iou = np.triu(oracle.iou_bev(b[order], b[order]), 1)
+            assert iou.max() <= 0.8 + 1e-5
+    # backbone output of the eval pass equals the oracle pipeline on the same clouds
+    from oracle import pipeline
+    frames = [f.cpu().numpy() for f in batch["points"]]
+    feats, coords, shape, _ = pipeline.backbone_forward(det.backbone_3d, frames, PC_RANGE, VOXEL_SIZE)
+    t = det.last_batch_dict["encoded_spconv_tensor"]
+    assert np.array_equal(t.indices.cpu().numpy(), coords)
+    assert float(np.abs(t.features.cpu().numpy() - feats).max()) <= TOL * max(1.0, float(np.abs(feats).max()))
