@@ -130,9 +130,7 @@ class MeanVFE(nn.Module):
                 vk, nk, ok = "voxels" + mm + fid, "voxel_num_points" + mm + fid, "voxel_features" + mm + fid
                 if mm and "mm" not in batch_dict:
                     continue
-                if ok in batch_dict and batch_dict[ok] is not None and vk not in batch_dict:
-                    continue
-                if vk not in batch_dict:
+                if batch_dict.get(vk) is None:      # absent, or the fused voxelizer already produced voxel_features
                     continue
                 feat = self._mean(batch_dict[vk], batch_dict[nk])
                 if self.model == "max" and not mm:
