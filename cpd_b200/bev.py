@@ -468,6 +468,6 @@ class CenterHead(nn.Module):
             if self.predict_boxes_when_training:
                 rois, roi_scores, roi_labels = self.reorder_rois_for_refining(data_dict["batch_size"], boxes)
                 data_dict.update(rois=rois, roi_scores=roi_scores, roi_labels=roi_labels, has_class_labels=True)
-            else:
-                data_dict["final_box_dicts"] = boxes
+            if not self.training or not self.predict_boxes_when_training:
+                data_dict["final_box_dicts"] = boxes          # no RoI head downstream on this path
         return data_dict

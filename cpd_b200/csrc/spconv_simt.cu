@@ -15,6 +15,9 @@ int32_t gather_gemm_tc(const float *x, int64_t m_in, int32_t cin, const float *w
                        cudaStream_t stream);
 size_t gather_gemm_tc_workspace(int64_t m_out, int32_t cin, int32_t K, int32_t cout);
 bool gather_gemm_tc_supported(int32_t cin, int32_t K, int32_t cout);
+bool gather_wgrad_tc_supported(int32_t cin, int32_t K, int32_t cout);
+int32_t gather_wgrad_tc(const float *x, int32_t cin, const float *dy, int64_t m_out, int32_t cout, const int32_t *nbr,
+                        int32_t K, float *dw, cudaStream_t stream);
 
 namespace {
 
@@ -354,8 +357,8 @@ extern "C" int32_t cpd_gather_gemm(const float *x, int64_t m_in, int32_t cin, co
 extern "C" size_t cpd_gather_wgrad_workspace_bytes(int64_t, int32_t, int32_t, int32_t) { return 0; }
 
 extern "C" int32_t cpd_gather_wgrad(const float *x, int64_t m_in, int32_t cin, const float *dy, int64_t m_out,
-                                    int32_t cout, const int32_t *nbr, int32_t K, float *dw, float *dbias, void *,
-                                    size_t, cpd_stream_t stream_)
+                                    int32_t cout, const int32_t *nbr, int32_t K, float *dw, float *dbias, int32_t algo,
+                                    void *, size_t, cpd_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     CPD_REQUIRE(x && dy && nbr && dw, CPD_ERR_BAD_ARG, "cpd_gather_wgrad: null argument");
@@ -363,6 +366,17 @@ extern "C" int32_t cpd_gather_wgrad(const float *x, int64_t m_in, int32_t cin, c
     CPD_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)cout * K * cin, stream));
     if (dbias) CPD_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)cout, stream));
     if (m_out == 0) return CPD_OK;
+    bool tc = false;
+    if (algo == CPD_ALGO_TCGEN05) {
+        CPD_REQUIRE(gather_wgrad_tc_supported(cin, K, cout), CPD_ERR_UNSUPPORTED, "cpd_gather_wgrad: tcgen05 path needs cin,cout >= 16 and multiples of 4");
+        tc = true;
+    } else if (algo == CPD_ALGO_AUTO) {
+        tc = gather_wgrad_tc_supported(cin, K, cout);
+    }
+    if (tc) {
+        int32_t st = gather_wgrad_tc(x, cin, dy, m_out, cout, nbr, K, dw, stream);
+        if (st) return st;
+    }
     const int co_tiles = (int)div_up(cout, 64), ci_tiles = (int)div_up(cin, 64);
     int S = (int)div_up(148 * 4, (long long)K * co_tiles * ci_tiles);
     int max_s = (int)div_up(m_out, 256);
@@ -370,9 +384,11 @@ extern "C" int32_t cpd_gather_wgrad(const float *x, int64_t m_in, int32_t cin, c
     if (S < 1) S = 1;
     int rows_per_cta = (int)div_up(div_up(m_out, S), WG_R) * WG_R;
     S = (int)div_up(m_out, rows_per_cta);
-    dim3 grid(K, S, co_tiles * ci_tiles);
-    gather_wgrad_simt<<<grid, 256, 0, stream>>>(x, cin, dy, cout, nbr, K, m_out, rows_per_cta, ci_tiles, dw);
-    count_launch();
+    if (!tc) {
+        dim3 grid(K, S, co_tiles * ci_tiles);
+        gather_wgrad_simt<<<grid, 256, 0, stream>>>(x, cin, dy, cout, nbr, K, m_out, rows_per_cta, ci_tiles, dw);
+        count_launch();
+    }
     if (dbias) {
         int cw = 1;
         while (cw < cout && cw < 256) cw <<= 1;

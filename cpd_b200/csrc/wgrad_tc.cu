@@ -1,0 +1,293 @@
+// tcgen05 weight-gradient for sm_100a:  dW[co, k, ci] = sum_o dY[o, co] * X[nbr[o, k], ci]
+// (spconv Appendix A.5 `dW_k = sum_pairs dY[o] x[i]^T`; also the wgrad of the dense BEV convs).
+//
+// Per tap k this is a GEMM  D_k[cout x cin] = dY^T [cout x P_k] . Xg_k [P_k x cin]  whose
+// contraction runs over the PAIRS of the tap.  Both operands are "MN-major" for the tensor
+// core (rows of dY / X are contiguous along cout / cin, i.e. along M / N), which tcgen05
+// supports for tf32 through the MN-major SWIZZLE_128B canonical layout -- no transposes.
+//
+// One CTA = (tap k, slice of the output rows, 128-wide cout tile, <=256-wide cin tile):
+//   warps 0-3  scan their slice of the neighbour table 256 rows at a time, COMPACT the rows
+//              that have a neighbour at this tap into a pair list (ballot + prefix), then for
+//              every 32 pairs gather the dY rows (A) and the X rows (B), split into tf32
+//              hi/lo and store them in the MN-major swizzled layout;
+//   warp 4     issues 4 x 3 tcgen05.mma kind::tf32 (M=128, N=cin tile, K=8) per 32-pair block
+//              into separate main / correction TMEM accumulators (see spconv_tc.cu);
+//   warps 0-3  finally tcgen05.ld the tile and add it to dW with fp32 atomics (split-K over
+//              row slices; dW is zeroed by the host wrapper first).
+// cout tiles narrower than 128 are zero-padded (the MMA M is fixed at 128): these are the
+// small-channel, gather-bound layers where tensor time is irrelevant.
+#include "tc_common.cuh"
+
+namespace cpd {
+namespace {
+using namespace tc;
+
+constexpr int WM = 128;        // UMMA M = cout tile
+constexpr int KB = 32;         // pairs per k-block (4 MMA K-steps of 8)
+constexpr int WIN = 256;       // table rows scanned per compaction window
+constexpr int NPROD = 128;
+constexpr int NTHREADS = 160;
+constexpr uint32_t END_MARK = 0xffffffffu;
+
+__host__ __device__ constexpr int w_stages(int bn) { return bn >= 256 ? 2 : 3; }
+__host__ __device__ constexpr int w_stage_bytes(int bn) { return 2 * KB * WM * 4 + 2 * KB * bn * 4; }
+__host__ __device__ constexpr int w_nmain(int bn) { return bn <= 128 ? 2 : 1; }
+__host__ __device__ constexpr int w_tmem_cols(int bn)
+{
+    int need = (w_nmain(bn) + 1) * bn, c = 32;
+    while (c < need) c <<= 1;
+    return c;
+}
+
+// MN-major SWIZZLE_128B: 32-column (128 B) blocks LBO = 4096 B apart, 8-row K atoms SBO = 1024 B apart
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr)
+{
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+// byte offset of the 16-byte chunk holding columns [4*c4, 4*c4+4) of row r in a [32 rows x cols] MN-major tile
+__device__ __forceinline__ uint32_t swz_mn(int r, int c4) { return (uint32_t)((c4 >> 3) * 4096 + r * 128 + (((c4 & 7) ^ (r & 7)) << 4)); }
+
+struct WgArgs {
+    const float *x, *dy;
+    const int32_t *nbr;
+    float *dw;
+    long long m_out;
+    int cin, cout, K, rows_per_cta, ci_tiles;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_tc_kernel(WgArgs a)
+{
+    constexpr int STAGES = w_stages(BN), STAGE = w_stage_bytes(BN), NMAIN = w_nmain(BN);
+    constexpr int A_BYTES = KB * WM * 4, B_BYTES = KB * BN * 4;
+    // a_major = b_major = MN (bits 15, 16), fp32 accumulate, tf32 operands
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)(WM >> 4) << 24);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    int32_t *pair_o = reinterpret_cast<int32_t *>(tiles + STAGES * STAGE);      // [WIN]
+    int32_t *pair_i = pair_o + WIN;                                             // [WIN]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(pair_i + WIN);                // full[S], empty[S], accum
+    uint32_t *info = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);       // [S] k8 steps valid in the stage / END
+    uint32_t *misc = info + STAGES;                                             // [0] tmem base, [1..4] warp counts, [5] total
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum_bar = smem_u32(bars + 2 * STAGES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tap = blockIdx.x;
+    const int co0 = (blockIdx.z / a.ci_tiles) * WM, ci0 = (blockIdx.z % a.ci_tiles) * BN;
+    const long long r_begin = (long long)blockIdx.y * a.rows_per_cta;
+    const long long r_end = min(r_begin + (long long)a.rows_per_cta, a.m_out);
+
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, NPROD); mbar_init(empty0 + 8 * s, 1); }
+            mbar_init(accum_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        tmem_alloc(smem_u32(misc), w_tmem_cols(BN));
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = misc[0];
+
+    if (warp < 4) {
+        // ================= producers =================
+        int it = 0;   // k-blocks produced so far
+        for (long long w0 = r_begin; w0 < r_end; w0 += WIN) {
+            // ---- compact the active (row, neighbour) pairs of this window ----
+            int32_t idx[2];
+            unsigned bal[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const long long o = w0 + h * NPROD + tid;
+                idx[h] = o < r_end ? __ldg(a.nbr + o * a.K + tap) : -1;
+                bal[h] = __ballot_sync(0xffffffffu, idx[h] >= 0);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");                 // previous window's list fully consumed
+            if (lane == 0) { misc[1 + warp] = __popc(bal[0]); misc[5 + warp] = __popc(bal[1]); }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            int base0 = 0, base1 = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int c0 = misc[1 + w], c1 = misc[5 + w];
+                if (w < warp) { base0 += c0; base1 += c1; }
+                total += c0 + c1;
+            }
+            const int half0 = misc[1] + misc[2] + misc[3] + misc[4];
+            if (idx[0] >= 0) {
+                const int p = base0 + __popc(bal[0] & ((1u << lane) - 1u));
+                pair_o[p] = (int32_t)(w0 + tid - r_begin); pair_i[p] = idx[0];
+            }
+            if (idx[1] >= 0) {
+                const int p = half0 + base1 + __popc(bal[1] & ((1u << lane) - 1u));
+                pair_o[p] = (int32_t)(w0 + NPROD + tid - r_begin); pair_i[p] = idx[1];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // ---- one k-block per 32 pairs ----
+            for (int b0 = 0; b0 < total; b0 += KB, ++it) {
+                const int s = it % STAGES;
+                const int nvalid = min(KB, total - b0);
+                float4 av[(KB * WM / 4) / NPROD], bv[(KB * BN / 4) / NPROD];
+                // A: dY rows, 32 x 128 columns; 32 consecutive threads read one 512-byte row segment
+#pragma unroll
+                for (int j = 0; j < (KB * WM / 4) / NPROD; ++j) {
+                    const int r = (tid >> 5) + 4 * j, c4 = tid & 31;
+                    const int col = co0 + c4 * 4;
+                    av[j] = (r < nvalid && col < a.cout)
+                                ? __ldg(reinterpret_cast<const float4 *>(a.dy + (r_begin + pair_o[b0 + r]) * a.cout + col))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                // B: gathered X rows, 32 x BN columns
+#pragma unroll
+                for (int j = 0; j < (KB * BN / 4) / NPROD; ++j) {
+                    const int e = tid + NPROD * j, r = e / (BN / 4), c4 = e % (BN / 4);
+                    const int col = ci0 + c4 * 4;
+                    bv[j] = (r < nvalid && col < a.cin)
+                                ? __ldg(reinterpret_cast<const float4 *>(a.x + (size_t)pair_i[b0 + r] * a.cin + col))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
+                uint8_t *st = tiles + s * STAGE;
+#pragma unroll
+                for (int j = 0; j < (KB * WM / 4) / NPROD; ++j) {
+                    float4 h, l;
+                    split4(av[j], h, l);
+                    const uint32_t off = swz_mn((tid >> 5) + 4 * j, tid & 31);
+                    *reinterpret_cast<float4 *>(st + off) = h;
+                    *reinterpret_cast<float4 *>(st + A_BYTES + off) = l;
+                }
+#pragma unroll
+                for (int j = 0; j < (KB * BN / 4) / NPROD; ++j) {
+                    float4 h, l;
+                    split4(bv[j], h, l);
+                    const int e = tid + NPROD * j;
+                    const uint32_t off = swz_mn(e / (BN / 4), e % (BN / 4));
+                    *reinterpret_cast<float4 *>(st + 2 * A_BYTES + off) = h;
+                    *reinterpret_cast<float4 *>(st + 2 * A_BYTES + B_BYTES + off) = l;
+                }
+                if (tid == 0) info[s] = (uint32_t)((nvalid + 7) / 8);
+                fence_async_smem();
+                mbar_arrive(full0 + 8 * s);
+            }
+        }
+        // ---- end marker, then epilogue ----
+        {
+            const int s = it % STAGES;
+            mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
+            if (tid == 0) info[s] = END_MARK;
+            mbar_arrive(full0 + 8 * s);
+        }
+        if (it > 0) {
+            mbar_wait(accum_bar, 0);
+            tc_fence_after();
+            const int n_acc = (it < NMAIN ? it : NMAIN) + 1;
+            const int co = co0 + warp * 32 + lane;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                for (int acc = 0; acc < n_acc; ++acc) {
+                    const int slot = acc == n_acc - 1 ? NMAIN : acc;
+                    uint32_t u[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(slot * BN + c0), u);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(u[j]);
+                }
+                if (co < a.cout) {
+                    float *dst = a.dw + ((size_t)co * a.K + tap) * a.cin + ci0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (ci0 + c0 + j < a.cin && v[j] != 0.f) atomicAdd(dst + j, v[j]);
+                }
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ================= MMA issuer =================
+        int it = 0;
+        for (;; ++it) {
+            const int s = it % STAGES;
+            mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
+            const uint32_t k8n = *reinterpret_cast<volatile uint32_t *>(&info[s]);
+            if (k8n == END_MARK) break;
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t st = smem_u32(tiles + s * STAGE);
+                const uint64_t a_hi = make_desc_mn(st), a_lo = make_desc_mn(st + A_BYTES);
+                const uint64_t b_hi = make_desc_mn(st + 2 * A_BYTES), b_lo = make_desc_mn(st + 2 * A_BYTES + B_BYTES);
+                const uint32_t d_main = tmem_base + (uint32_t)((it % NMAIN) * BN), d_corr = tmem_base + (uint32_t)(NMAIN * BN);
+                for (uint32_t k8 = 0; k8 < k8n; ++k8) {
+                    const uint64_t adv = (uint64_t)((k8 * 1024) >> 4);     // next 8-row K atom
+                    umma_tf32(d_main, a_hi + adv, b_hi + adv, IDESC, (it >= NMAIN || k8) ? 1u : 0u);
+                    umma_tf32(d_corr, a_lo + adv, b_hi + adv, IDESC, (it | (int)k8) ? 1u : 0u);
+                    umma_tf32(d_corr, a_hi + adv, b_lo + adv, IDESC, 1u);
+                }
+                umma_commit(empty0 + 8 * s);
+            }
+            __syncwarp();
+        }
+        if (it > 0 && lane == 0) umma_commit(accum_bar);
+        __syncwarp();
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, w_tmem_cols(BN));
+    }
+}
+
+template <int BN>
+size_t wg_smem() { return 1024 + (size_t)w_stages(BN) * w_stage_bytes(BN) + 2 * WIN * 4 + (2 * w_stages(BN) + 1) * 8 + (w_stages(BN) + 16) * 4; }
+
+template <int BN>
+int32_t launch_wg(const WgArgs &a, dim3 grid, cudaStream_t stream)
+{
+    static bool configured = false;
+    if (!configured) {
+        CPD_CUDA(cudaFuncSetAttribute(gather_wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem<BN>()));
+        configured = true;
+    }
+    gather_wgrad_tc_kernel<BN><<<grid, NTHREADS, wg_smem<BN>(), stream>>>(a);
+    count_launch();
+    return launch_status("cpd_gather_wgrad[tcgen05]");
+}
+
+}  // namespace
+
+bool gather_wgrad_tc_supported(int32_t cin, int32_t K, int32_t cout)
+{
+    return cin % 4 == 0 && cout % 4 == 0 && cin >= 16 && cout >= 16 && K <= 64;
+}
+
+// dw must be zeroed by the caller (split-K atomics).
+int32_t gather_wgrad_tc(const float *x, int32_t cin, const float *dy, int64_t m_out, int32_t cout, const int32_t *nbr,
+                        int32_t K, float *dw, cudaStream_t stream)
+{
+    CPD_REQUIRE(gather_wgrad_tc_supported(cin, K, cout), CPD_ERR_UNSUPPORTED, "tcgen05 wgrad: unsupported shape");
+    CPD_REQUIRE((((uintptr_t)x | (uintptr_t)dy) & 15) == 0, CPD_ERR_MISALIGNED, "tcgen05 wgrad: pointers must be 16-byte aligned");
+    const int bn = cin <= 32 ? 32 : cin <= 64 ? 64 : cin <= 128 ? 128 : 256;
+    const int ci_tiles = (int)div_up(cin, bn), co_tiles = (int)div_up(cout, WM);
+    int S = (int)div_up(148 * 2, (long long)K * ci_tiles * co_tiles);
+    const int max_s = (int)div_up(m_out, 4 * WIN);
+    if (S > max_s) S = max_s;
+    if (S < 1) S = 1;
+    int rows = (int)(div_up(div_up(m_out, S), WIN) * WIN);
+    S = (int)div_up(m_out, rows);
+    WgArgs a{x, dy, nbr, dw, m_out, cin, cout, K, rows, ci_tiles};
+    dim3 grid(K, S, ci_tiles * co_tiles);
+    switch (bn) {
+        case 32: return launch_wg<32>(a, grid, stream);
+        case 64: return launch_wg<64>(a, grid, stream);
+        case 128: return launch_wg<128>(a, grid, stream);
+        default: return launch_wg<256>(a, grid, stream);
+    }
+}
+
+}  // namespace cpd

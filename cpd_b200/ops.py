@@ -201,7 +201,7 @@ def gather_gemm(x, w, nbr, bias=None, scale=None, shift=None, residual=None, rel
     return y
 
 
-def gather_wgrad(x, dy, nbr, want_bias=False):
+def gather_wgrad(x, dy, nbr, want_bias=False, algo=ALGO_AUTO):
     """dw (cout, K, cin), dbias (cout,) | None."""
     _need_cuda(x, dy, nbr)
     L = _lib.lib()
@@ -215,7 +215,7 @@ def gather_wgrad(x, dy, nbr, want_bias=False):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     _lib.check(L.cpd_gather_wgrad(_ptr(x), x.shape[0], cin, _ptr(dy), dy.shape[0], cout, _ptr(nbr), K, _ptr(dw), _ptr(db),
-                                  _ptr(ws), wsb, _stream()), "cpd_gather_wgrad")
+                                  int(algo), _ptr(ws), wsb, _stream()), "cpd_gather_wgrad")
     if PROFILE is not None:
         e1.record()
         PROFILE.append((e0, e1, dict(kind="gather_wgrad", m_in=x.shape[0], m_out=dy.shape[0], cin=cin, cout=cout, K=K, nbr=nbr,

@@ -137,7 +137,7 @@ CPD_API size_t cpd_gather_gemm_workspace_bytes(int64_t m_out, int32_t cin, int32
 /* Weight-gradient: dw[co, k, ci] = sum_o dy[o, co] * x[nbr[o, k], ci]; dw is overwritten.
  * dbias (NULL ok): dbias[co] = sum_o dy[o, co]. */
 CPD_API int32_t cpd_gather_wgrad(const float *x, int64_t m_in, int32_t cin, const float *dy, int64_t m_out,
-                         int32_t cout, const int32_t *nbr, int32_t K, float *dw, float *dbias,
+                         int32_t cout, const int32_t *nbr, int32_t K, float *dw, float *dbias, int32_t algo,
                          void *ws, size_t ws_bytes, cpd_stream_t stream);
 CPD_API size_t cpd_gather_wgrad_workspace_bytes(int64_t m_out, int32_t cin, int32_t K, int32_t cout);
 
