@@ -4,7 +4,7 @@
 // Per tap k this is a GEMM  D_k[cout x cin] = dY^T [cout x P_k] . Xg_k [P_k x cin]  whose
 // contraction runs over the PAIRS of the tap.  Both operands are "MN-major" for the tensor
 // core (rows of dY / X are contiguous along cout / cin, i.e. along M / N), which tcgen05
-// supports for tf32 through the MN-major SWIZZLE_128B canonical layout -- no transposes.
+// supports for tf32 through the MN-major SWIZZLE_128B_BASE32B canonical layout -- no transposes.
 //
 // One CTA = (tap k, slice of the output rows, 128-wide cout tile, <=256-wide cin tile):
 //   warps 0-3  scan their slice of the neighbour table 256 rows at a time, COMPACT the rows
@@ -40,14 +40,22 @@ __host__ __device__ constexpr int w_tmem_cols(int bn)
     return c;
 }
 
-// MN-major SWIZZLE_128B: 32-column (128 B) blocks LBO = 4096 B apart, 8-row K atoms SBO = 1024 B apart
+// MN-major tf32 operands have exactly one legal shared-memory layout: SWIZZLE_128B_BASE32B
+// (descriptor layout type 1; CUTLASS: "for mn-major tf32 operands, SW128_32B is the only available
+// smem layout").  Atom = 4 K-rows x 128 B (32 consecutive M/N elements per row); the 32-byte chunk
+// index (address bits 5-6) is XOR-ed with the row index inside the atom (address bits 7-8).
+// Tile = [32 pair rows x cols]: 32-column blocks LBO = 4096 B apart, 4-row atoms SBO = 512 B apart.
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr)
 {
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           (1ull << 46) | (2ull << 61);
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+           (1ull << 46) | (1ull << 61);
 }
 // byte offset of the 16-byte chunk holding columns [4*c4, 4*c4+4) of row r in a [32 rows x cols] MN-major tile
-__device__ __forceinline__ uint32_t swz_mn(int r, int c4) { return (uint32_t)((c4 >> 3) * 4096 + r * 128 + (((c4 & 7) ^ (r & 7)) << 4)); }
+__device__ __forceinline__ uint32_t swz_mn(int r, int c4)
+{
+    const int c32 = (c4 & 7) >> 1;                       // 32-byte chunk inside the 128-byte row
+    return (uint32_t)((c4 >> 3) * 4096 + r * 128 + ((c32 ^ (r & 3)) << 5) + ((c4 & 1) << 4));
+}
 
 struct WgArgs {
     const float *x, *dy;
