@@ -249,6 +249,14 @@ def run_ours(a):
         g["bytes"] += 4.0 * (m["m_in"] * m["cin"] + m["m_out"] * m["cout"]) + 8.0 * P + 4.0 * m["K"] * m["cin"] * m["cout"]
         g["flops"] += 2.0 * P * m["cin"] * m["cout"]
     gg_ms = sum(g["ms"] for g in groups.values())
+    if os.environ.get("CPD_BENCH_GROUPS"):
+        rows = sorted(((k, g) for k, g in groups.items()), key=lambda kv: -kv[1]["ms"])
+        with open(os.environ["CPD_BENCH_GROUPS"], "w") as f:
+            f.write(f"# per-step totals over {a.steps} timed steps; step = {total_ms / a.steps:.2f} ms\n")
+            f.write("kind cin cout K launches/step ms/step us/launch GB/s(algorithmic) TFLOP/s(useful)\n")
+            for k, g in rows:
+                f.write(f"{k[0]} {k[1]} {k[2]} {k[3]} {g['n'] / a.steps:.1f} {g['ms'] / a.steps:.3f} {1e3 * g['ms'] / g['n']:.1f} "
+                        f"{g['bytes'] / g['ms'] / 1e6:.0f} {g['flops'] / g['ms'] / 1e9:.1f}\n")
     top_key, top = max(groups.items(), key=lambda kv: kv[1]["ms"])
     ai = top["flops"] / max(top["bytes"], 1.0)
     tf32_peak = bf16 / 2.0

@@ -37,6 +37,7 @@ constexpr int NTHREADS = 160; // + MMA warp
 constexpr int MAX_TAPS = 32;
 
 __host__ __device__ constexpr int stages_for(int bn) { return bn >= 256 ? 2 : bn >= 128 ? 3 : 2; }
+__host__ __device__ constexpr int ctas_per_sm(int bn) { return bn <= 64 ? 2 : 1; }
 __host__ __device__ constexpr int stage_bytes(int bn) { return 2 * BM * BK * 4 + 2 * bn * BK * 4; }
 // TMEM accumulators per tile: n_main(bn) "main" ones (A_hi.B_hi, k-blocks dealt round-robin) + 1
 // "correction" one (A_lo.B_hi + A_hi.B_lo, ~2^-11 of the main magnitude).  The tensor core
@@ -79,7 +80,7 @@ struct TcArgs {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
+__global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kernel(TcArgs a)
 {
     constexpr int STAGES = stages_for(BN);
     constexpr int NMAIN = n_main(BN);
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long row0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;                    // output-channel tile (cout > 256 is split over grid.y)
 
     if (tid == 0) misc[1] = 0u;
     if (warp == 4) {
@@ -131,35 +133,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
 
     if (warp < 4) {
         // ================= producers =================
+        // Software-pipelined: the gather loads of k-block it+1 are in flight while k-block it is
+        // split and stored (register double buffering; single-buffered for BN=256 to stay under 255 regs).
         const int c = tid & 7, r_base = tid >> 3;   // 16-byte chunk, first row (rows r_base + 16 j)
-        int it = 0;
-        for (int k = 0; k < a.K; ++k) {
-            if (!((tap_mask >> k) & 1u)) continue;
-            for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                const int s = it % STAGES;
-                const int col = kb * BK + c * 4;
-                const bool col_ok = col < a.cin;
+        auto load = [&](int it, float4(&av)[BM / 16], float4(&bv)[BN / 16]) {
+            const int k = __fns(tap_mask, 0, it / kblocks + 1);      // it/kblocks-th active tap
+            const int col = (it % kblocks) * BK + c * 4;
+            const bool col_ok = col < a.cin;
+#pragma unroll
+            for (int j = 0; j < BM / 16; ++j) {
+                const int32_t idx = nbr_s[k * BM + r_base + 16 * j];
+                av[j] = (idx >= 0 && col_ok) ? __ldg(reinterpret_cast<const float4 *>(a.x + (size_t)idx * a.cin + col))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < BN / 16; ++j) {
+                const int n = n0 + r_base + 16 * j;
+                bv[j] = col_ok ? __ldg(reinterpret_cast<const float4 *>(a.w + ((size_t)n * a.K + k) * a.cin + col))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto store = [&](int it, const float4(&av)[BM / 16], const float4(&bv)[BN / 16]) {
+            const int s = it % STAGES;
+            mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
+            uint8_t *st = tiles + s * STAGE;
+#pragma unroll
+            for (int j = 0; j < BM / 16; ++j) split_store(st, st + A_BYTES, swz(r_base + 16 * j, c), av[j]);
+#pragma unroll
+            for (int j = 0; j < BN / 16; ++j) split_store(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, swz(r_base + 16 * j, c), bv[j]);
+            fence_async_smem();
+            mbar_arrive(full0 + 8 * s);
+        };
+        if constexpr (BN <= 128) {
+            if (n_iters > 0) {
+                float4 a0[BM / 16], b0[BN / 16], a1[BM / 16], b1[BN / 16];
+                load(0, a0, b0);
+                for (int it = 0; it < n_iters; it += 2) {
+                    if (it + 1 < n_iters) load(it + 1, a1, b1);
+                    store(it, a0, b0);
+                    if (it + 1 < n_iters) {
+                        if (it + 2 < n_iters) load(it + 2, a0, b0);
+                        store(it + 1, a1, b1);
+                    }
+                }
+            }
+        } else {
+            for (int it = 0; it < n_iters; ++it) {
                 float4 av[BM / 16], bv[BN / 16];
-#pragma unroll
-                for (int j = 0; j < BM / 16; ++j) {
-                    const int32_t idx = nbr_s[k * BM + r_base + 16 * j];
-                    av[j] = (idx >= 0 && col_ok) ? __ldg(reinterpret_cast<const float4 *>(a.x + (size_t)idx * a.cin + col))
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int j = 0; j < BN / 16; ++j) {
-                    const int n = r_base + 16 * j;
-                    bv[j] = col_ok ? __ldg(reinterpret_cast<const float4 *>(a.w + ((size_t)n * a.K + k) * a.cin + col))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
-                uint8_t *st = tiles + s * STAGE;
-#pragma unroll
-                for (int j = 0; j < BM / 16; ++j) split_store(st, st + A_BYTES, swz(r_base + 16 * j, c), av[j]);
-#pragma unroll
-                for (int j = 0; j < BN / 16; ++j) split_store(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, swz(r_base + 16 * j, c), bv[j]);
-                fence_async_smem();
-                mbar_arrive(full0 + 8 * s);
+                load(it, av, bv);
+                store(it, av, bv);
             }
         }
         // ================= epilogue =================
@@ -194,7 +216,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
                 o.x = v[4 * q + 0]; o.y = v[4 * q + 1];
                 o.z = v[4 * q + 2]; o.w = v[4 * q + 3];
                 if (a.bias) {
-                    const float4 b = __ldg(reinterpret_cast<const float4 *>(a.bias + c0 + 4 * q));
+                    const float4 b = __ldg(reinterpret_cast<const float4 *>(a.bias + n0 + c0 + 4 * q));
                     o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                 }
                 *reinterpret_cast<float4 *>(stage_out + my_row * OUT_LD + c0 + 4 * q) = o;
@@ -206,22 +228,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
             float s = 0.f, q = 0.f;
             const int rows = (int)min((long long)BM, a.m_out - row0);
             for (int r = 0; r < rows; ++r) { float t = stage_out[r * OUT_LD + tid]; s += t; q += t * t; }
-            atomicAdd(a.stats + tid, s);
-            atomicAdd(a.stats + a.cout + tid, q);
+            atomicAdd(a.stats + n0 + tid, s);
+            atomicAdd(a.stats + a.cout + n0 + tid, q);
         }
         if (BN > NPROD && a.stats && tid + NPROD < BN) {
             float s = 0.f, q = 0.f;
             const int rows = (int)min((long long)BM, a.m_out - row0);
             for (int r = 0; r < rows; ++r) { float t = stage_out[r * OUT_LD + tid + NPROD]; s += t; q += t * t; }
-            atomicAdd(a.stats + tid + NPROD, s);
-            atomicAdd(a.stats + a.cout + tid + NPROD, q);
+            atomicAdd(a.stats + n0 + tid + NPROD, s);
+            atomicAdd(a.stats + a.cout + n0 + tid + NPROD, q);
         }
         constexpr int V_PER_ROW = BN / 4;
         for (int t = tid; t < BM * V_PER_ROW; t += NPROD) {
-            const int r = t / V_PER_ROW, cv = (t % V_PER_ROW) * 4;
+            const int r = t / V_PER_ROW, cl = (t % V_PER_ROW) * 4, cv = n0 + cl;
             const long long row = row0 + r;
             if (row >= a.m_out) break;
-            float4 o = *reinterpret_cast<const float4 *>(stage_out + r * OUT_LD + cv);
+            float4 o = *reinterpret_cast<const float4 *>(stage_out + r * OUT_LD + cl);
             if (a.scale) {
                 const float4 sc = __ldg(reinterpret_cast<const float4 *>(a.scale + cv));
                 const float4 sh = __ldg(reinterpret_cast<const float4 *>(a.shift + cv));
@@ -279,7 +301,8 @@ int32_t launch_tc(const TcArgs &a, cudaStream_t stream)
         CPD_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    gather_gemm_tc_kernel<BN><<<(unsigned)div_up(a.m_out, BM), NTHREADS, smem_bytes<BN>(a.K), stream>>>(a);
+    dim3 grid((unsigned)div_up(a.m_out, BM), (unsigned)(a.cout / BN));
+    gather_gemm_tc_kernel<BN><<<grid, NTHREADS, smem_bytes<BN>(a.K), stream>>>(a);
     count_launch();
     return launch_status("cpd_gather_gemm[tcgen05]");
 }
@@ -288,7 +311,8 @@ int32_t launch_tc(const TcArgs &a, cudaStream_t stream)
 
 bool gather_gemm_tc_supported(int32_t cin, int32_t K, int32_t cout)
 {
-    return cin % 8 == 0 && cin >= 8 && K <= MAX_TAPS && (cout == 16 || cout == 32 || cout == 64 || cout == 128 || cout == 256);
+    return cin % 8 == 0 && cin >= 8 && K <= MAX_TAPS &&
+           (cout == 16 || cout == 32 || cout == 64 || cout == 128 || (cout >= 256 && cout % 256 == 0 && cout <= 2048));
 }
 
 size_t gather_gemm_tc_workspace(int64_t, int32_t, int32_t, int32_t) { return 16; }

@@ -25,12 +25,14 @@ using namespace tc;
 
 constexpr int WM = 128;        // UMMA M = cout tile
 constexpr int KB = 32;         // pairs per k-block (4 MMA K-steps of 8)
-constexpr int WIN = 256;       // table rows scanned per compaction window
+constexpr int WIN = 512;       // table rows scanned per compaction window
+constexpr int RPT = WIN / 128; // table rows per producer thread per window
 constexpr int NPROD = 128;
 constexpr int NTHREADS = 160;
 constexpr uint32_t END_MARK = 0xffffffffu;
 
-__host__ __device__ constexpr int w_stages(int bn) { return bn >= 256 ? 2 : 3; }
+__host__ __device__ constexpr int w_stages(int bn) { return bn == 128 ? 3 : 2; }
+__host__ __device__ constexpr int w_ctas_per_sm(int bn) { return bn <= 64 ? 2 : 1; }
 __host__ __device__ constexpr int w_stage_bytes(int bn) { return 2 * KB * WM * 4 + 2 * KB * bn * 4; }
 __host__ __device__ constexpr int w_nmain(int bn) { return bn <= 128 ? 2 : 1; }
 __host__ __device__ constexpr int w_tmem_cols(int bn)
@@ -66,10 +68,11 @@ struct WgArgs {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_tc_kernel(WgArgs a)
+__global__ void __launch_bounds__(NTHREADS, w_ctas_per_sm(BN)) gather_wgrad_tc_kernel(WgArgs a)
 {
     constexpr int STAGES = w_stages(BN), STAGE = w_stage_bytes(BN), NMAIN = w_nmain(BN);
     constexpr int A_BYTES = KB * WM * 4, B_BYTES = KB * BN * 4;
+    constexpr int A_V = (KB * WM / 4) / NPROD, B_V = (KB * BN / 4) / NPROD;   // float4 loads per thread per k-block
     // a_major = b_major = MN (bits 15, 16), fp32 accumulate, tf32 operands
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
                                ((uint32_t)(WM >> 4) << 24);
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_tc_kernel(WgArgs a)
     int32_t *pair_i = pair_o + WIN;                                             // [WIN]
     uint64_t *bars = reinterpret_cast<uint64_t *>(pair_i + WIN);                // full[S], empty[S], accum
     uint32_t *info = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);       // [S] k8 steps valid in the stage / END
-    uint32_t *misc = info + STAGES;                                             // [0] tmem base, [1..4] warp counts, [5] total
+    uint32_t *misc = info + STAGES;                                             // [0] tmem base, [1..16] per-warp pair counts
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum_bar = smem_u32(bars + 2 * STAGES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -105,82 +108,112 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_tc_kernel(WgArgs a)
 
     if (warp < 4) {
         // ================= producers =================
+        // The table entries of the NEXT window and the operand rows of the NEXT k-block are
+        // prefetched into registers while the current k-block is split and stored.
         int it = 0;   // k-blocks produced so far
-        for (long long w0 = r_begin; w0 < r_end; w0 += WIN) {
-            // ---- compact the active (row, neighbour) pairs of this window ----
-            int32_t idx[2];
-            unsigned bal[2];
+        auto load_table = [&](long long w0, int32_t(&idx)[RPT]) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < RPT; ++h) {
                 const long long o = w0 + h * NPROD + tid;
                 idx[h] = o < r_end ? __ldg(a.nbr + o * a.K + tap) : -1;
-                bal[h] = __ballot_sync(0xffffffffu, idx[h] >= 0);
             }
+        };
+        auto load = [&](int b0, int total, float4(&av)[A_V], float4(&bv)[B_V]) {
+            const int nvalid = min(KB, total - b0);
+#pragma unroll
+            for (int j = 0; j < A_V; ++j) {       // A: dY rows, 32 x 128 cols; a warp reads one 512-byte row segment
+                const int r = (tid >> 5) + 4 * j, col = co0 + (tid & 31) * 4;
+                av[j] = (r < nvalid && col < a.cout)
+                            ? __ldg(reinterpret_cast<const float4 *>(a.dy + (r_begin + pair_o[b0 + r]) * a.cout + col))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < B_V; ++j) {       // B: gathered X rows, 32 x BN cols
+                const int e = tid + NPROD * j, r = e / (BN / 4), col = ci0 + (e % (BN / 4)) * 4;
+                bv[j] = (r < nvalid && col < a.cin)
+                            ? __ldg(reinterpret_cast<const float4 *>(a.x + (size_t)pair_i[b0 + r] * a.cin + col))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto store = [&](int b0, int total, const float4(&av)[A_V], const float4(&bv)[B_V]) {
+            const int s = it % STAGES;
+            mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
+            uint8_t *st = tiles + s * STAGE;
+#pragma unroll
+            for (int j = 0; j < A_V; ++j) {
+                float4 h, l;
+                split4(av[j], h, l);
+                const uint32_t off = swz_mn((tid >> 5) + 4 * j, tid & 31);
+                *reinterpret_cast<float4 *>(st + off) = h;
+                *reinterpret_cast<float4 *>(st + A_BYTES + off) = l;
+            }
+#pragma unroll
+            for (int j = 0; j < B_V; ++j) {
+                float4 h, l;
+                split4(bv[j], h, l);
+                const int e = tid + NPROD * j;
+                const uint32_t off = swz_mn(e / (BN / 4), e % (BN / 4));
+                *reinterpret_cast<float4 *>(st + 2 * A_BYTES + off) = h;
+                *reinterpret_cast<float4 *>(st + 2 * A_BYTES + B_BYTES + off) = l;
+            }
+            if (tid == 0) info[s] = (uint32_t)((min(KB, total - b0) + 7) / 8);
+            fence_async_smem();
+            mbar_arrive(full0 + 8 * s);
+            ++it;
+        };
+        int32_t idx_next[RPT];
+        load_table(r_begin, idx_next);
+        for (long long w0 = r_begin; w0 < r_end; w0 += WIN) {
+            // ---- compact the active (row, neighbour) pairs of this window ----
+            int32_t idx[RPT];
+            unsigned bal[RPT];
+#pragma unroll
+            for (int h = 0; h < RPT; ++h) { idx[h] = idx_next[h]; bal[h] = __ballot_sync(0xffffffffu, idx[h] >= 0); }
             asm volatile("bar.sync 1, 128;" ::: "memory");                 // previous window's list fully consumed
-            if (lane == 0) { misc[1 + warp] = __popc(bal[0]); misc[5 + warp] = __popc(bal[1]); }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            int base0 = 0, base1 = 0, total = 0;
+            if (lane == 0) {
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const int c0 = misc[1 + w], c1 = misc[5 + w];
-                if (w < warp) { base0 += c0; base1 += c1; }
-                total += c0 + c1;
-            }
-            const int half0 = misc[1] + misc[2] + misc[3] + misc[4];
-            if (idx[0] >= 0) {
-                const int p = base0 + __popc(bal[0] & ((1u << lane) - 1u));
-                pair_o[p] = (int32_t)(w0 + tid - r_begin); pair_i[p] = idx[0];
-            }
-            if (idx[1] >= 0) {
-                const int p = half0 + base1 + __popc(bal[1] & ((1u << lane) - 1u));
-                pair_o[p] = (int32_t)(w0 + NPROD + tid - r_begin); pair_i[p] = idx[1];
+                for (int h = 0; h < RPT; ++h) misc[1 + h * 4 + warp] = __popc(bal[h]);
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            // ---- one k-block per 32 pairs ----
-            for (int b0 = 0; b0 < total; b0 += KB, ++it) {
-                const int s = it % STAGES;
-                const int nvalid = min(KB, total - b0);
-                float4 av[(KB * WM / 4) / NPROD], bv[(KB * BN / 4) / NPROD];
-                // A: dY rows, 32 x 128 columns; 32 consecutive threads read one 512-byte row segment
+            int total = 0, mybase[RPT];
 #pragma unroll
-                for (int j = 0; j < (KB * WM / 4) / NPROD; ++j) {
-                    const int r = (tid >> 5) + 4 * j, c4 = tid & 31;
-                    const int col = co0 + c4 * 4;
-                    av[j] = (r < nvalid && col < a.cout)
-                                ? __ldg(reinterpret_cast<const float4 *>(a.dy + (r_begin + pair_o[b0 + r]) * a.cout + col))
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                // B: gathered X rows, 32 x BN columns
+            for (int h = 0; h < RPT; ++h) {
 #pragma unroll
-                for (int j = 0; j < (KB * BN / 4) / NPROD; ++j) {
-                    const int e = tid + NPROD * j, r = e / (BN / 4), c4 = e % (BN / 4);
-                    const int col = ci0 + c4 * 4;
-                    bv[j] = (r < nvalid && col < a.cin)
-                                ? __ldg(reinterpret_cast<const float4 *>(a.x + (size_t)pair_i[b0 + r] * a.cin + col))
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int w = 0; w < 4; ++w) {
+                    const int cnt = misc[1 + h * 4 + w];
+                    if (w == warp) mybase[h] = total;
+                    total += cnt;
                 }
-                mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
-                uint8_t *st = tiles + s * STAGE;
+            }
 #pragma unroll
-                for (int j = 0; j < (KB * WM / 4) / NPROD; ++j) {
-                    float4 h, l;
-                    split4(av[j], h, l);
-                    const uint32_t off = swz_mn((tid >> 5) + 4 * j, tid & 31);
-                    *reinterpret_cast<float4 *>(st + off) = h;
-                    *reinterpret_cast<float4 *>(st + A_BYTES + off) = l;
+            for (int h = 0; h < RPT; ++h) {
+                if (idx[h] >= 0) {
+                    const int p = mybase[h] + __popc(bal[h] & ((1u << lane) - 1u));
+                    pair_o[p] = (int32_t)(w0 + h * NPROD + tid - r_begin); pair_i[p] = idx[h];
                 }
-#pragma unroll
-                for (int j = 0; j < (KB * BN / 4) / NPROD; ++j) {
-                    float4 h, l;
-                    split4(bv[j], h, l);
-                    const int e = tid + NPROD * j;
-                    const uint32_t off = swz_mn(e / (BN / 4), e % (BN / 4));
-                    *reinterpret_cast<float4 *>(st + 2 * A_BYTES + off) = h;
-                    *reinterpret_cast<float4 *>(st + 2 * A_BYTES + B_BYTES + off) = l;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (w0 + WIN < r_end) load_table(w0 + WIN, idx_next);
+            // ---- one k-block per 32 pairs, register double-buffered ----
+            if constexpr (BN <= 128) {
+                if (total > 0) {
+                    float4 a0[A_V], b0v[B_V], a1[A_V], b1v[B_V];
+                    load(0, total, a0, b0v);
+                    for (int b0 = 0; b0 < total; b0 += 2 * KB) {
+                        if (b0 + KB < total) load(b0 + KB, total, a1, b1v);
+                        store(b0, total, a0, b0v);
+                        if (b0 + KB < total) {
+                            if (b0 + 2 * KB < total) load(b0 + 2 * KB, total, a0, b0v);
+                            store(b0 + KB, total, a1, b1v);
+                        }
+                    }
                 }
-                if (tid == 0) info[s] = (uint32_t)((nvalid + 7) / 8);
-                fence_async_smem();
-                mbar_arrive(full0 + 8 * s);
+            } else {
+                for (int b0 = 0; b0 < total; b0 += KB) {
+                    float4 av[A_V], bv[B_V];
+                    load(b0, total, av, bv);
+                    store(b0, total, av, bv);
+                }
             }
         }
         // ---- end marker, then epilogue ----
@@ -252,7 +285,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_tc_kernel(WgArgs a)
 }
 
 template <int BN>
-size_t wg_smem() { return 1024 + (size_t)w_stages(BN) * w_stage_bytes(BN) + 2 * WIN * 4 + (2 * w_stages(BN) + 1) * 8 + (w_stages(BN) + 16) * 4; }
+size_t wg_smem() { return 1024 + (size_t)w_stages(BN) * w_stage_bytes(BN) + 2 * WIN * 4 + (2 * w_stages(BN) + 1) * 8 + (w_stages(BN) + 32) * 4; }
 
 template <int BN>
 int32_t launch_wg(const WgArgs &a, dim3 grid, cudaStream_t stream)
@@ -271,7 +304,7 @@ int32_t launch_wg(const WgArgs &a, dim3 grid, cudaStream_t stream)
 
 bool gather_wgrad_tc_supported(int32_t cin, int32_t K, int32_t cout)
 {
-    return cin % 4 == 0 && cout % 4 == 0 && cin >= 16 && cout >= 16 && K <= 64;
+    return cin % 4 == 0 && cout % 4 == 0 && cin >= 8 && cout >= 8 && K <= 64;
 }
 
 // dw must be zeroed by the caller (split-K atomics).

@@ -193,13 +193,21 @@ class SparseConvolution(SparseModule):
         if self.inverse or self.transposed:
             raise NotImplementedError("SparseInverseConv3d forward is not part of the CPD hot path")
         rb, out_hash = self.get_rulebook(inp)
-        feats = _GatherConv.apply(inp.features, self.weight, self.bias, rb, self.algo)
+        x, w = inp.features, self.weight
+        if self.in_channels % 8:          # e.g. the 5 raw point features: zero-pad to a multiple of 8 so the
+            pad = 8 - self.in_channels % 8    # vectorised / tensor-core kernels apply (zeros contribute nothing)
+            x, w = torch.nn.functional.pad(x, (0, pad)), torch.nn.functional.pad(w, (0, pad))
+        feats = _GatherConv.apply(x, w, self.bias, rb, self.algo)
         return self._wrap_output(inp, rb, out_hash, feats)
 
     def forward_fused(self, inp, scale, shift, relu, residual=None):
         """Inference-only: conv + folded BatchNorm affine (+ residual) (+ ReLU) in one kernel."""
         rb, out_hash = self.get_rulebook(inp)
-        feats = ops.gather_gemm(inp.features, self.weight, rb.nbr_fwd, bias=self.bias, scale=scale, shift=shift,
+        x, w = inp.features, self.weight
+        if self.in_channels % 8:
+            pad = 8 - self.in_channels % 8
+            x, w = torch.nn.functional.pad(x, (0, pad)), torch.nn.functional.pad(w, (0, pad))
+        feats = ops.gather_gemm(x, w, rb.nbr_fwd, bias=self.bias, scale=scale, shift=shift,
                                 residual=residual, relu=relu, algo=self.algo)
         return self._wrap_output(inp, rb, out_hash, feats)
 
