@@ -25,7 +25,7 @@ SIGNATURES = {
     "cpd_rulebook_strided_tables": (_i32, [_vp, _i64, _vp, _vp, _sz, _vp, _i64, _vp, _vp, _sz, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cpd_gather_gemm": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
     "cpd_gather_gemm_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32]),
-    "cpd_gather_wgrad": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "cpd_gather_wgrad": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
     "cpd_gather_wgrad_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "cpd_weight_transpose": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "cpd_conv2d_table": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),

@@ -18,7 +18,7 @@ size_t gather_gemm_tc_workspace(int64_t m_out, int32_t cin, int32_t K, int32_t c
 bool gather_gemm_tc_supported(int32_t cin, int32_t K, int32_t cout);
 bool gather_wgrad_tc_supported(int32_t cin, int32_t K, int32_t cout);
 int32_t gather_wgrad_tc(const float *x, int32_t cin, const float *dy, int64_t m_out, int32_t cout, const int32_t *nbr,
-                        int32_t K, float *dw, cudaStream_t stream);
+                        int32_t K, int32_t tap_major, float *dw, cudaStream_t stream);
 
 namespace {
 
@@ -182,7 +182,8 @@ constexpr int WG_R = 16;
 __global__ void __launch_bounds__(256) gather_wgrad_simt(const float *__restrict__ x, int cin,
                                                          const float *__restrict__ dy, int cout,
                                                          const int32_t *__restrict__ nbr, int K, long long m_out,
-                                                         int rows_per_cta, int ci_tiles, float *__restrict__ dw)
+                                                         int rows_per_cta, int ci_tiles, int tap_major,
+                                                         float *__restrict__ dw)
 {
     __shared__ __align__(16) float dyS[WG_R * 64];
     __shared__ __align__(16) float xS[WG_R * 64];
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(256) gather_wgrad_simt(const float *__restrict
         int have = 0;
         if (tid < WG_R) {
             long long row = r0 + tid;
-            int32_t idx = row < r_end ? __ldg(nbr + row * K + tap) : -1;
+            int32_t idx = row < r_end ? __ldg(nbr + (tap_major ? (long long)tap * m_out + row : row * K + tap)) : -1;
             idxS[tid] = idx;
             have = idx >= 0;
         }
@@ -359,8 +360,8 @@ extern "C" int32_t cpd_gather_gemm(const float *x, int64_t m_in, int32_t cin, co
 extern "C" size_t cpd_gather_wgrad_workspace_bytes(int64_t, int32_t, int32_t, int32_t) { return 0; }
 
 extern "C" int32_t cpd_gather_wgrad(const float *x, int64_t m_in, int32_t cin, const float *dy, int64_t m_out,
-                                    int32_t cout, const int32_t *nbr, int32_t K, float *dw, float *dbias, int32_t algo,
-                                    void *, size_t, cpd_stream_t stream_)
+                                    int32_t cout, const int32_t *nbr, int32_t nbr_tap_major, int32_t K, float *dw,
+                                    float *dbias, int32_t algo, void *, size_t, cpd_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     CPD_REQUIRE(x && dy && nbr && dw, CPD_ERR_BAD_ARG, "cpd_gather_wgrad: null argument");
@@ -376,7 +377,7 @@ extern "C" int32_t cpd_gather_wgrad(const float *x, int64_t m_in, int32_t cin, c
         tc = gather_wgrad_tc_supported(cin, K, cout);
     }
     if (tc) {
-        int32_t st = gather_wgrad_tc(x, cin, dy, m_out, cout, nbr, K, dw, stream);
+        int32_t st = gather_wgrad_tc(x, cin, dy, m_out, cout, nbr, K, nbr_tap_major, dw, stream);
         if (st) return st;
     }
     const int co_tiles = (int)div_up(cout, 64), ci_tiles = (int)div_up(cin, 64);
@@ -388,7 +389,7 @@ extern "C" int32_t cpd_gather_wgrad(const float *x, int64_t m_in, int32_t cin, c
     S = (int)div_up(m_out, rows_per_cta);
     if (!tc) {
         dim3 grid(K, S, co_tiles * ci_tiles);
-        gather_wgrad_simt<<<grid, 256, 0, stream>>>(x, cin, dy, cout, nbr, K, m_out, rows_per_cta, ci_tiles, dw);
+        gather_wgrad_simt<<<grid, 256, 0, stream>>>(x, cin, dy, cout, nbr, K, m_out, rows_per_cta, ci_tiles, nbr_tap_major, dw);
         count_launch();
     }
     if (dbias) {

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kern
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     int32_t *nbr_s = reinterpret_cast<int32_t *>(tiles + STAGES * STAGE);          // [K][BM]
     uint64_t *bars = reinterpret_cast<uint64_t *>(nbr_s + a.K * BM);              // full[S], empty[S], accum
-    uint32_t *misc = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);         // [0] tmem base, [1] tap mask
+    uint32_t *misc = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);         // [0] tmem base, [1] tap mask, [2..] active tap list
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum_bar = smem_u32(bars + 2 * STAGES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -130,14 +130,19 @@ __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kern
     const uint32_t tap_mask = misc[1];
     const int kblocks = (a.cin + BK - 1) / BK;
     const int n_iters = __popc(tap_mask) * kblocks;
+    if (tid < a.K && ((tap_mask >> tid) & 1u)) misc[2 + __popc(tap_mask & ((1u << tid) - 1u))] = (uint32_t)tid;   // compact tap list
+    asm volatile("bar.sync 2, 160;" ::: "memory");
 
     if (warp < 4) {
         // ================= producers =================
         // Software-pipelined: the gather loads of k-block it+1 are in flight while k-block it is
         // split and stored (register double buffering; single-buffered for BN=256 to stay under 255 regs).
         const int c = tid & 7, r_base = tid >> 3;   // 16-byte chunk, first row (rows r_base + 16 j)
+        uint32_t soff[BM / 16];                     // swizzled byte offsets of this thread's chunks (loop invariant;
+#pragma unroll                                      //  the B tile uses the first BN/16 of them)
+        for (int j = 0; j < BM / 16; ++j) soff[j] = swz(r_base + 16 * j, c);
         auto load = [&](int it, float4(&av)[BM / 16], float4(&bv)[BN / 16]) {
-            const int k = __fns(tap_mask, 0, it / kblocks + 1);      // it/kblocks-th active tap
+            const int k = (int)misc[2 + it / kblocks];               // it/kblocks-th active tap
             const int col = (it % kblocks) * BK + c * 4;
             const bool col_ok = col < a.cin;
 #pragma unroll
@@ -158,9 +163,10 @@ __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kern
             mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
             uint8_t *st = tiles + s * STAGE;
 #pragma unroll
-            for (int j = 0; j < BM / 16; ++j) split_store(st, st + A_BYTES, swz(r_base + 16 * j, c), av[j]);
+            for (int j = 0; j < BM / 16; ++j) split_store(st, st + A_BYTES, soff[j], av[j]);
 #pragma unroll
-            for (int j = 0; j < BN / 16; ++j) split_store(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, swz(r_base + 16 * j, c), bv[j]);
+            for (int j = 0; j < BN / 16; ++j)      // rows r_base + 16 j; 128 rows = 16 KB of swizzled tile
+                split_store(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, soff[j & 7] + (uint32_t)(j >> 3) * 16384u, bv[j]);
             fence_async_smem();
             mbar_arrive(full0 + 8 * s);
         };
@@ -290,7 +296,7 @@ __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kern
 }
 
 template <int BN>
-size_t smem_bytes(int K) { return 1024 + (size_t)stages_for(BN) * stage_bytes(BN) + (size_t)K * BM * 4 + (2 * stages_for(BN) + 1) * 8 + 16; }
+size_t smem_bytes(int K) { return 1024 + (size_t)stages_for(BN) * stage_bytes(BN) + (size_t)K * BM * 4 + (2 * stages_for(BN) + 1) * 8 + (2 + MAX_TAPS) * 4; }
 
 template <int BN>
 int32_t launch_tc(const TcArgs &a, cudaStream_t stream)

@@ -64,7 +64,7 @@ struct WgArgs {
     const int32_t *nbr;
     float *dw;
     long long m_out;
-    int cin, cout, K, rows_per_cta, ci_tiles;
+    int cin, cout, K, rows_per_cta, ci_tiles, tap_major;
 };
 
 template <int BN>
@@ -107,6 +107,21 @@ __global__ void __launch_bounds__(NTHREADS, w_ctas_per_sm(BN)) gather_wgrad_tc_k
     const uint32_t tmem_base = misc[0];
 
     if (warp < 4) {
+        // Zero all operand stages once: column ranges beyond cout / cin (M is padded to 128, N to BN) are
+        // never written again, which removes most of the shared-memory store traffic of narrow layers.
+        for (int e = tid; e < STAGES * STAGE / 16; e += NPROD) reinterpret_cast<float4 *>(tiles)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const bool a_live = co0 + (tid & 31) * 4 < a.cout;            // this thread's A columns exist
+        uint32_t a_off[A_V], b_off[B_V];
+        bool b_live[B_V];
+#pragma unroll
+        for (int j = 0; j < A_V; ++j) a_off[j] = swz_mn((tid >> 5) + 4 * j, tid & 31);
+#pragma unroll
+        for (int j = 0; j < B_V; ++j) {
+            const int e = tid + NPROD * j;
+            b_off[j] = swz_mn(e / (BN / 4), e % (BN / 4));
+            b_live[j] = ci0 + (e % (BN / 4)) * 4 < a.cin;
+        }
         // ================= producers =================
         // The table entries of the NEXT window and the operand rows of the NEXT k-block are
         // prefetched into registers while the current k-block is split and stored.
@@ -115,7 +130,7 @@ __global__ void __launch_bounds__(NTHREADS, w_ctas_per_sm(BN)) gather_wgrad_tc_k
 #pragma unroll
             for (int h = 0; h < RPT; ++h) {
                 const long long o = w0 + h * NPROD + tid;
-                idx[h] = o < r_end ? __ldg(a.nbr + o * a.K + tap) : -1;
+                idx[h] = o < r_end ? __ldg(a.nbr + (a.tap_major ? (long long)tap * a.m_out + o : o * a.K + tap)) : -1;
             }
         };
         auto load = [&](int b0, int total, float4(&av)[A_V], float4(&bv)[B_V]) {
@@ -123,14 +138,14 @@ __global__ void __launch_bounds__(NTHREADS, w_ctas_per_sm(BN)) gather_wgrad_tc_k
 #pragma unroll
             for (int j = 0; j < A_V; ++j) {       // A: dY rows, 32 x 128 cols; a warp reads one 512-byte row segment
                 const int r = (tid >> 5) + 4 * j, col = co0 + (tid & 31) * 4;
-                av[j] = (r < nvalid && col < a.cout)
+                av[j] = (a_live && r < nvalid)
                             ? __ldg(reinterpret_cast<const float4 *>(a.dy + (r_begin + pair_o[b0 + r]) * a.cout + col))
                             : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int j = 0; j < B_V; ++j) {       // B: gathered X rows, 32 x BN cols
                 const int e = tid + NPROD * j, r = e / (BN / 4), col = ci0 + (e % (BN / 4)) * 4;
-                bv[j] = (r < nvalid && col < a.cin)
+                bv[j] = (b_live[j] && r < nvalid)
                             ? __ldg(reinterpret_cast<const float4 *>(a.x + (size_t)pair_i[b0 + r] * a.cin + col))
                             : make_float4(0.f, 0.f, 0.f, 0.f);
             }
@@ -139,22 +154,22 @@ __global__ void __launch_bounds__(NTHREADS, w_ctas_per_sm(BN)) gather_wgrad_tc_k
             const int s = it % STAGES;
             mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
             uint8_t *st = tiles + s * STAGE;
+            if (a_live) {
 #pragma unroll
-            for (int j = 0; j < A_V; ++j) {
-                float4 h, l;
-                split4(av[j], h, l);
-                const uint32_t off = swz_mn((tid >> 5) + 4 * j, tid & 31);
-                *reinterpret_cast<float4 *>(st + off) = h;
-                *reinterpret_cast<float4 *>(st + A_BYTES + off) = l;
+                for (int j = 0; j < A_V; ++j) {
+                    float4 h, l;
+                    split4(av[j], h, l);
+                    *reinterpret_cast<float4 *>(st + a_off[j]) = h;
+                    *reinterpret_cast<float4 *>(st + A_BYTES + a_off[j]) = l;
+                }
             }
 #pragma unroll
             for (int j = 0; j < B_V; ++j) {
+                if (!b_live[j]) continue;
                 float4 h, l;
                 split4(bv[j], h, l);
-                const int e = tid + NPROD * j;
-                const uint32_t off = swz_mn(e / (BN / 4), e % (BN / 4));
-                *reinterpret_cast<float4 *>(st + 2 * A_BYTES + off) = h;
-                *reinterpret_cast<float4 *>(st + 2 * A_BYTES + B_BYTES + off) = l;
+                *reinterpret_cast<float4 *>(st + 2 * A_BYTES + b_off[j]) = h;
+                *reinterpret_cast<float4 *>(st + 2 * A_BYTES + B_BYTES + b_off[j]) = l;
             }
             if (tid == 0) info[s] = (uint32_t)((min(KB, total - b0) + 7) / 8);
             fence_async_smem();
@@ -309,7 +324,7 @@ bool gather_wgrad_tc_supported(int32_t cin, int32_t K, int32_t cout)
 
 // dw must be zeroed by the caller (split-K atomics).
 int32_t gather_wgrad_tc(const float *x, int32_t cin, const float *dy, int64_t m_out, int32_t cout, const int32_t *nbr,
-                        int32_t K, float *dw, cudaStream_t stream)
+                        int32_t K, int32_t tap_major, float *dw, cudaStream_t stream)
 {
     CPD_REQUIRE(gather_wgrad_tc_supported(cin, K, cout), CPD_ERR_UNSUPPORTED, "tcgen05 wgrad: unsupported shape");
     CPD_REQUIRE((((uintptr_t)x | (uintptr_t)dy) & 15) == 0, CPD_ERR_MISALIGNED, "tcgen05 wgrad: pointers must be 16-byte aligned");
@@ -321,7 +336,7 @@ int32_t gather_wgrad_tc(const float *x, int32_t cin, const float *dy, int64_t m_
     if (S < 1) S = 1;
     int rows = (int)(div_up(div_up(m_out, S), WIN) * WIN);
     S = (int)div_up(m_out, rows);
-    WgArgs a{x, dy, nbr, dw, m_out, cin, cout, K, rows, ci_tiles};
+    WgArgs a{x, dy, nbr, dw, m_out, cin, cout, K, rows, ci_tiles, tap_major};
     dim3 grid(K, S, ci_tiles * co_tiles);
     switch (bn) {
         case 32: return launch_wg<32>(a, grid, stream);

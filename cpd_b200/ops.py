@@ -201,12 +201,13 @@ def gather_gemm(x, w, nbr, bias=None, scale=None, shift=None, residual=None, rel
     return y
 
 
-def gather_wgrad(x, dy, nbr, want_bias=False, algo=ALGO_AUTO):
-    """dw (cout, K, cin), dbias (cout,) | None."""
+def gather_wgrad(x, dy, nbr, want_bias=False, algo=ALGO_AUTO, tap_major=False):
+    """dw (cout, K, cin), dbias (cout,) | None.  tap_major: nbr is the transposed (K, m_out) table."""
     _need_cuda(x, dy, nbr)
     L = _lib.lib()
     x, dy = _f32c(x), _f32c(dy)
-    cin, cout, K = x.shape[1], dy.shape[1], nbr.shape[1]
+    cin, cout, K = x.shape[1], dy.shape[1], nbr.shape[0 if tap_major else 1]
+    assert nbr.is_contiguous() and nbr.shape[1 if tap_major else 0] == dy.shape[0]
     dw = torch.empty((cout, K, cin), dtype=torch.float32, device=x.device)
     db = torch.empty((cout,), dtype=torch.float32, device=x.device) if want_bias else None
     wsb = L.cpd_gather_wgrad_workspace_bytes(dy.shape[0], cin, K, cout)
@@ -214,8 +215,8 @@ def gather_wgrad(x, dy, nbr, want_bias=False, algo=ALGO_AUTO):
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    _lib.check(L.cpd_gather_wgrad(_ptr(x), x.shape[0], cin, _ptr(dy), dy.shape[0], cout, _ptr(nbr), K, _ptr(dw), _ptr(db),
-                                  int(algo), _ptr(ws), wsb, _stream()), "cpd_gather_wgrad")
+    _lib.check(L.cpd_gather_wgrad(_ptr(x), x.shape[0], cin, _ptr(dy), dy.shape[0], cout, _ptr(nbr), int(bool(tap_major)), K,
+                                  _ptr(dw), _ptr(db), int(algo), _ptr(ws), wsb, _stream()), "cpd_gather_wgrad")
     if PROFILE is not None:
         e1.record()
         PROFILE.append((e0, e1, dict(kind="gather_wgrad", m_in=x.shape[0], m_out=dy.shape[0], cin=cin, cout=cout, K=K, nbr=nbr,

@@ -35,6 +35,13 @@ class Rulebook:
         self.in_shape, self.out_shape = in_shape, out_shape
         self.ksize, self.stride, self.padding = ksize, stride, padding
         self.out_hash = None                # coordinate hash of out_coords (strided only)
+        self._nbr_fwd_t = None              # (K, m_out) transposed table for the weight-gradient kernel
+
+    @property
+    def nbr_fwd_t(self):
+        if self._nbr_fwd_t is None:
+            self._nbr_fwd_t = self.nbr_fwd.t().contiguous()
+        return self._nbr_fwd_t
 
 
 class SparseConvTensor:
@@ -120,7 +127,10 @@ class _GatherConv(torch.autograd.Function):
                 wt = ops.weight_transpose(weight, flip_taps=False)
                 dx = ops.gather_gemm(dy, wt, rb.nbr_bwd, algo=ctx.algo)
         if ctx.needs_input_grad[1] or ctx.has_bias:
-            dw, db = ops.gather_wgrad(x, dy, rb.nbr_fwd, want_bias=ctx.has_bias)
+            if rb.nbr_fwd.shape[1] > 1:
+                dw, db = ops.gather_wgrad(x, dy, rb.nbr_fwd_t, want_bias=ctx.has_bias, tap_major=True)
+            else:
+                dw, db = ops.gather_wgrad(x, dy, rb.nbr_fwd, want_bias=ctx.has_bias)
             dw = dw.view_as(weight)
         return dx, dw, db, None, None
 

@@ -135,10 +135,11 @@ CPD_API int32_t cpd_gather_gemm(const float *x, int64_t m_in, int32_t cin, const
 CPD_API size_t cpd_gather_gemm_workspace_bytes(int64_t m_out, int32_t cin, int32_t K, int32_t cout, int32_t algo);
 
 /* Weight-gradient: dw[co, k, ci] = sum_o dy[o, co] * x[nbr[o, k], ci]; dw is overwritten.
- * dbias (NULL ok): dbias[co] = sum_o dy[o, co]. */
+ * dbias (NULL ok): dbias[co] = sum_o dy[o, co].  nbr_tap_major != 0: nbr is the transposed
+ * (K, m_out) table (coalesced per-tap scans; what the tcgen05 kernel prefers). */
 CPD_API int32_t cpd_gather_wgrad(const float *x, int64_t m_in, int32_t cin, const float *dy, int64_t m_out,
-                         int32_t cout, const int32_t *nbr, int32_t K, float *dw, float *dbias, int32_t algo,
-                         void *ws, size_t ws_bytes, cpd_stream_t stream);
+                         int32_t cout, const int32_t *nbr, int32_t nbr_tap_major, int32_t K, float *dw,
+                         float *dbias, int32_t algo, void *ws, size_t ws_bytes, cpd_stream_t stream);
 CPD_API size_t cpd_gather_wgrad_workspace_bytes(int64_t m_out, int32_t cin, int32_t K, int32_t cout);
 
 /* (cout, K, cin) -> (cin, K, cout), optionally reversing the tap order (the operand of

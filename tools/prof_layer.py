@@ -26,7 +26,9 @@ x, dy = torch.randn(m, c, device=dev), torch.randn(m, c, device=dev)
 w = torch.randn(c, 27, c, device=dev) * 0.05
 print(f"stage {stage}: M={m} C={c} P={P} ({P / m:.1f} nbrs/row), shape {t.spatial_shape}")
 byt = 4.0 * (2 * m * c) + 8.0 * P + 4.0 * 27 * c * c
-for name, fn in (("gather_gemm", lambda: ops.gather_gemm(x, w, nbr)), ("gather_wgrad", lambda: ops.gather_wgrad(x, dy, nbr))):
+nbr_t = nbr.t().contiguous()
+for name, fn in (("gather_gemm", lambda: ops.gather_gemm(x, w, nbr)), ("gather_wgrad", lambda: ops.gather_wgrad(x, dy, nbr)),
+                 ("gather_wgrad tap-major", lambda: ops.gather_wgrad(x, dy, nbr_t, tap_major=True))):
     fn(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -19,6 +19,9 @@ for (m_in, m_out, cin, cout, K, dens) in cases:
         nbr[:, 5] = -1
     ref, _ = ops.gather_wgrad(x, dy, nbr, algo=ops.ALGO_SIMT)
     got, _ = ops.gather_wgrad(x, dy, nbr, algo=ops.ALGO_TCGEN05)
+    nbr_t = nbr.t().contiguous()
+    got_t, _ = ops.gather_wgrad(x, dy, nbr_t, algo=ops.ALGO_TCGEN05, tap_major=True)
+    ref_t, _ = ops.gather_wgrad(x, dy, nbr_t, algo=ops.ALGO_SIMT, tap_major=True)
     torch.cuda.synchronize()
     ex = torch.zeros(cout, K, cin, dtype=torch.float64, device=dev)
     for k in range(K):
@@ -36,7 +39,15 @@ for (m_in, m_out, cin, cout, K, dens) in cases:
         ms = e0.elapsed_time(e1) / 3
         P = int((nbr >= 0).sum())
         print(f"   {name}: {ms*1e3:9.1f} us  {2.0*P*cin*cout/ms/1e9:7.1f} TFLOP/s (useful)  {P*(cin+cout)*4/ms/1e6:7.0f} GB/s gathered", flush=True)
-    good = e_tc < 1e-4
+    e_t = max((got_t.double() - ex).abs().max().item(), (ref_t.double() - ex).abs().max().item()) / scale
+    for name, tbl, tm in (("tc tap-major", nbr_t, True),):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            ops.gather_wgrad(x, dy, tbl, algo=ops.ALGO_TCGEN05, tap_major=tm)
+        e1.record(); torch.cuda.synchronize()
+        print(f"   {name}: {e0.elapsed_time(e1) / 3 * 1e3:9.1f} us", flush=True)
+    good = e_tc < 1e-4 and e_t < 1e-4
     ok &= good
     print(f"m_out={m_out} cin={cin} cout={cout} K={K}: rel err vs fp64 tc={e_tc:.2e} simt={e_simt:.2e} (|dw|max {scale:.1f}) {'OK' if good else 'FAIL'}", flush=True)
 print("ALL OK" if ok else "SOME FAILED")
