@@ -62,6 +62,9 @@ class SparseBasicBlock(sp.SparseModule):
             s2, h2 = fold_bn(self.bn2)
             out = self.conv1.forward_fused(x, s1, h1, relu=True)
             return self.conv2.forward_fused(out, s2, h2, relu=True, residual=x.features)
+        if self.downsample is None and sp.bn_fusable(self.bn1) and sp.bn_fusable(self.bn2):
+            out = self.conv1.forward_bn_train(x, self.bn1, relu=True)
+            return self.conv2.forward_bn_train(out, self.bn2, relu=True, residual=x.features)
         identity = x
         out = self.conv1(x)
         out = out.replace_feature(self.relu(self.bn1(out.features)))

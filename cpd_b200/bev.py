@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 from . import iou3d_nms_utils, ops
 from .backbone import _cfg
-from .sparse import Rulebook, _GatherConv, fold_bn
+from .sparse import Rulebook, _BNTrain, _GatherConv, bn_fusable, fold_bn
 
 
 class DenseMap:
@@ -89,6 +89,12 @@ class DenseConv2d(nn.Module):
             y = _GatherConv.apply(x.data, self.w_kc().contiguous(), self.bias, rb, self.algo)
         return DenseMap(y, x.n, ho, wo)
 
+    def forward_bn_train(self, x, bn, relu):
+        """Training: conv emitting batch statistics, then one fused normalise(+ReLU) pass."""
+        rb, ho, wo = pixel_tables(x.n, x.h, x.w, self.k, self.k, self.stride, self.padding, x.data.device)
+        y, stats = _GatherConv.apply(x.data, self.w_kc().contiguous(), self.bias, rb, self.algo, True)
+        return DenseMap(_BNTrain.apply(y, stats, bn.weight, bn.bias, None, bn, relu), x.n, ho, wo)
+
 
 class DenseConvTranspose2d(nn.Module):
     """nn.ConvTranspose2d with kernel == stride (base_bev_backbone.py:48-59): every output pixel
@@ -140,6 +146,10 @@ class DenseSequential(nn.Sequential):
                     sc, sh = fold_bn(bn) if bn is not None else (None, None)
                     x = m(x, scale=sc, shift=sh, relu=has_relu)
                     i += 1 + (bn is not None) + has_relu
+                    continue
+                if isinstance(m, DenseConv2d) and bn is not None and bn_fusable(bn):
+                    x = m.forward_bn_train(x, bn, has_relu)
+                    i += 2 + has_relu
                     continue
                 x = m(x)
             elif isinstance(m, nn.BatchNorm2d):

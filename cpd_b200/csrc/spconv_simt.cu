@@ -346,7 +346,7 @@ extern "C" int32_t cpd_gather_gemm(const float *x, int64_t m_in, int32_t cin, co
         CPD_REQUIRE(gather_gemm_tc_supported(cin, K, cout), CPD_ERR_UNSUPPORTED, "cpd_gather_gemm: tcgen05 path needs cin%%8==0, cout%%16==0, cout<=256");
         tc = true;
     } else if (algo == CPD_ALGO_AUTO) {
-        static const int min_cin = getenv("CPD_TC_MIN_CIN") ? atoi(getenv("CPD_TC_MIN_CIN")) : 32;   // tuning knob
+        static const int min_cin = getenv("CPD_TC_MIN_CIN") ? atoi(getenv("CPD_TC_MIN_CIN")) : 16;   // tuning knob
         tc = gather_gemm_tc_supported(cin, K, cout) && cin >= min_cin && ws && ws_bytes >= gather_gemm_tc_workspace(m_out, cin, K, cout);
     }
     if (tc) return gather_gemm_tc(x, m_in, cin, w, K, cout, nbr, m_out, bias, scale, shift, residual, relu, stats, y, ws, ws_bytes, stream);

@@ -301,3 +301,35 @@ def nms_mask(boxes_sorted, thresh, rotated=True):
     mask = torch.zeros((n, cb), dtype=torch.int64, device=b.device)
     _lib.check(L.cpd_nms_mask(_ptr(b), n, float(thresh), int(bool(rotated)), _ptr(mask), _stream()), "cpd_nms_mask")
     return mask
+
+
+# ------------------------------------------------------------------------------------
+# fused training-mode BatchNorm (+ReLU, + residual) on row matrices
+# ------------------------------------------------------------------------------------
+def bn_train_fwd(x, stats, gamma, beta, residual, relu, eps, momentum, running_mean, running_var):
+    """-> (y, mean_invstd (2,c)).  stats (2,c) = per-channel sum / sum of squares of x (from gather_gemm)."""
+    _need_cuda(x, stats)
+    L = _lib.lib()
+    x = _f32c(x)
+    m, c = x.shape
+    y = torch.empty_like(x)
+    mi = torch.empty((2, c), dtype=torch.float32, device=x.device)
+    residual = _f32c(residual) if residual is not None else None
+    _lib.check(L.cpd_bn_train_fwd(_ptr(x), m, c, _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(residual), int(bool(relu)),
+                                  float(eps), float(momentum), _ptr(running_mean), _ptr(running_var), _ptr(mi), _ptr(y),
+                                  _stream()), "cpd_bn_train_fwd")
+    return y, mi
+
+
+def bn_train_bwd(x, y, dy, mean_invstd, gamma, relu, want_residual):
+    """-> (dx, dresidual | None, dgamma, dbeta)."""
+    _need_cuda(x, dy)
+    L = _lib.lib()
+    dy = _f32c(dy)
+    m, c = x.shape
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_residual else None
+    gb = torch.empty((2, c), dtype=torch.float32, device=x.device)
+    _lib.check(L.cpd_bn_train_bwd(_ptr(x), _ptr(y), _ptr(dy), m, c, _ptr(mean_invstd), _ptr(gamma), int(bool(relu)), _ptr(dx),
+                                  _ptr(dres), _ptr(gb), _stream()), "cpd_bn_train_bwd")
+    return dx, dres, gb[1], gb[0]

@@ -104,17 +104,23 @@ class _ToDense(torch.autograd.Function):
 
 
 class _GatherConv(torch.autograd.Function):
-    """y = gather-GEMM(x, W, nbr) (+bias); backward = dgrad gather-GEMM + wgrad (Appendix A.5)."""
+    """y = gather-GEMM(x, W, nbr) (+bias); backward = dgrad gather-GEMM + wgrad (Appendix A.5).
+    With want_stats the epilogue also returns the per-channel (sum, sum of squares) of y for a fused BatchNorm."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, rb, algo):
+    def forward(ctx, x, weight, bias, rb, algo, want_stats=False):
         ctx.rb, ctx.algo = rb, algo
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        return ops.gather_gemm(x, weight, rb.nbr_fwd, bias=bias, algo=algo)
+        stats = torch.zeros((2, weight.shape[0]), dtype=torch.float32, device=x.device) if want_stats else None
+        y = ops.gather_gemm(x, weight, rb.nbr_fwd, bias=bias, stats=stats, algo=algo)
+        if not want_stats:
+            return y
+        ctx.mark_non_differentiable(stats)
+        return y, stats
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, *unused):
         x, weight = ctx.saved_tensors
         rb = ctx.rb
         dy = dy.contiguous()
@@ -132,7 +138,34 @@ class _GatherConv(torch.autograd.Function):
             else:
                 dw, db = ops.gather_wgrad(x, dy, rb.nbr_fwd, want_bias=ctx.has_bias)
             dw = dw.view_as(weight)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
+
+
+class _BNTrain(torch.autograd.Function):
+    """Training-mode BatchNorm (+residual) (+ReLU) on a row matrix, statistics supplied by the conv epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, stats, gamma, beta, residual, bn, relu):
+        y, mi = ops.bn_train_fwd(x, stats, gamma, beta, residual, relu, bn.eps, bn.momentum if bn.momentum is not None else 0.1,
+                                 bn.running_mean if bn.track_running_stats else None,
+                                 bn.running_var if bn.track_running_stats else None)
+        if bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        ctx.relu, ctx.has_res = relu, residual is not None
+        ctx.save_for_backward(x, y if relu else None, mi, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mi, gamma = ctx.saved_tensors
+        dx, dres, dgamma, dbeta = ops.bn_train_bwd(x, y, dy, mi, gamma, ctx.relu, ctx.has_res)
+        return dx, None, (dgamma if gamma is not None else None), (dbeta if gamma is not None else None), dres, None, None
+
+
+def bn_fusable(bn):
+    """A BatchNorm layer whose training-mode forward can take its statistics from the conv epilogue."""
+    return isinstance(bn, (nn.BatchNorm1d, nn.BatchNorm2d)) and bn.training and bn.affine and bn.num_features % 4 == 0 \
+        and bn.num_features <= 1024 and torch.is_grad_enabled()
 
 
 class SparseModule(nn.Module):
@@ -208,6 +241,19 @@ class SparseConvolution(SparseModule):
             pad = 8 - self.in_channels % 8    # vectorised / tensor-core kernels apply (zeros contribute nothing)
             x, w = torch.nn.functional.pad(x, (0, pad)), torch.nn.functional.pad(w, (0, pad))
         feats = _GatherConv.apply(x, w, self.bias, rb, self.algo)
+        return self._wrap_output(inp, rb, out_hash, feats)
+
+    def forward_bn_train(self, inp, bn, relu, residual=None):
+        """Training: conv (epilogue emits the batch statistics) -> ONE normalise(+residual)(+ReLU) pass."""
+        rb, out_hash = self.get_rulebook(inp)
+        x, w = inp.features, self.weight
+        if self.in_channels % 8:
+            pad = 8 - self.in_channels % 8
+            x, w = torch.nn.functional.pad(x, (0, pad)), torch.nn.functional.pad(w, (0, pad))
+        y, stats = _GatherConv.apply(x, w, self.bias, rb, self.algo, True)
+        if y.shape[0] == 0:
+            return self._wrap_output(inp, rb, out_hash, y)
+        feats = _BNTrain.apply(y, stats, bn.weight, bn.bias, residual, bn, relu)
         return self._wrap_output(inp, rb, out_hash, feats)
 
     def forward_fused(self, inp, scale, shift, relu, residual=None):
@@ -288,6 +334,12 @@ class SparseSequential(SparseModule):
                 relu = i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)
                 scale, shift = fold_bn(mods[i + 1])
                 x = m.forward_fused(x, scale, shift, relu)
+                i += 3 if relu else 2
+                continue
+            if isinstance(m, SparseConvolution) and not m.inverse and isinstance(x, SparseConvTensor) \
+                    and i + 1 < len(mods) and bn_fusable(mods[i + 1]):
+                relu = i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)
+                x = m.forward_bn_train(x, mods[i + 1], relu)
                 i += 3 if relu else 2
                 continue
             if isinstance(m, SparseModule):

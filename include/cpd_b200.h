@@ -142,6 +142,22 @@ CPD_API int32_t cpd_gather_wgrad(const float *x, int64_t m_in, int32_t cin, cons
                          float *dbias, int32_t algo, void *ws, size_t ws_bytes, cpd_stream_t stream);
 CPD_API size_t cpd_gather_wgrad_workspace_bytes(int64_t m_out, int32_t cin, int32_t K, int32_t cout);
 
+/* Training-mode BatchNorm on a row matrix x (m, c), fused with ReLU and the residual add: replaces
+ * nn.BatchNorm1d/2d + nn.ReLU (+ `out + identity`) after the convolutions
+ * (cpd/models/backbones_3d/spconv_backbone.py:13-35,100-136,410; base_bev_backbone.py:31-59;
+ * center_head.py:22-27,73-80).  stats (2, c) = per-channel sum and sum of squares of x as accumulated
+ * by cpd_gather_gemm; mean_invstd (2, c) is written for the backward; running_* (NULL ok) follow
+ * torch semantics (momentum, unbiased variance).  y = relu?((x-mean)*invstd*gamma+beta (+residual)). */
+CPD_API int32_t cpd_bn_train_fwd(const float *x, int64_t m, int32_t c, const float *stats, const float *gamma,
+                         const float *beta, const float *residual, int32_t relu, float eps, float momentum,
+                         float *running_mean, float *running_var, float *mean_invstd, float *y,
+                         cpd_stream_t stream);
+/* dz = dy*(y>0) if relu; dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)); dresidual (NULL ok) = dz;
+ * dgamma_dbeta (2, c): row 0 = dbeta = sum dz, row 1 = dgamma = sum dz*xhat. */
+CPD_API int32_t cpd_bn_train_bwd(const float *x, const float *y, const float *dy, int64_t m, int32_t c,
+                         const float *mean_invstd, const float *gamma, int32_t relu, float *dx,
+                         float *dresidual, float *dgamma_dbeta, cpd_stream_t stream);
+
 /* (cout, K, cin) -> (cin, K, cout), optionally reversing the tap order (the operand of
  * the input-gradient: SubM reuses its own table with flipped taps). */
 CPD_API int32_t cpd_weight_transpose(const float *w, int32_t cout, int32_t K, int32_t cin, int32_t flip_taps,

@@ -301,3 +301,39 @@ def test_res_backbone_train_step_gradients(oracle, cuda):
     assert np.abs(x.features.grad.cpu().numpy() - gx).max() <= TOL
     assert np.abs(conv.weight.grad.cpu().numpy() - gw).max() <= TOL * max(1.0, np.abs(gw).max())
     assert np.abs(conv.bias.grad.cpu().numpy() - gb).max() <= TOL * max(1.0, np.abs(gb).max())
+
+
+# ------------------------------------------------------------------------------- fused training BatchNorm
+@pytest.mark.parametrize("m,c,relu,res", [(5000, 16, True, False), (70001, 128, True, True), (333, 64, False, False), (20000, 256, True, False)])
+def test_fused_bn_train_matches_torch(cuda, m, c, relu, res):
+    """conv-epilogue statistics + cpd_bn_train_fwd/bwd against nn.BatchNorm1d (+ residual) (+ ReLU) in float64."""
+    from cpd_b200 import sparse as sp
+    torch.manual_seed(m + c)
+    x = (torch.randn(m, c, device=cuda) * 1.7 + 0.3).requires_grad_(True)
+    r = torch.randn(m, c, device=cuda, requires_grad=True) if res else None
+    bn = torch.nn.BatchNorm1d(c, eps=1e-3, momentum=0.01).to(cuda).train()
+    bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.uniform_(-0.3, 0.3)
+    ref = torch.nn.BatchNorm1d(c, eps=1e-3, momentum=0.01).double().train()
+    ref.load_state_dict({k: v.double().cpu() if v.is_floating_point() else v.cpu() for k, v in bn.state_dict().items()})
+    stats = torch.stack([x.detach().sum(0), (x.detach() ** 2).sum(0)])            # what the conv epilogue would emit
+    y = sp._BNTrain.apply(x, stats, bn.weight, bn.bias, r, bn, relu)
+    xr = x.detach().double().cpu().requires_grad_(True)
+    rr = r.detach().double().cpu().requires_grad_(True) if res else None
+    yr = ref(xr)
+    if res:
+        yr = yr + rr
+    if relu:
+        yr = torch.relu(yr)
+    assert float((y.detach().double().cpu() - yr.detach()).abs().max()) <= TOL
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    yr.backward(dy.double().cpu())
+    sc = lambda t: max(1.0, float(t.abs().max()))
+    assert float((x.grad.double().cpu() - xr.grad).abs().max()) <= TOL * sc(xr.grad)
+    assert float((bn.weight.grad.double().cpu() - ref.weight.grad).abs().max()) <= TOL * sc(ref.weight.grad)
+    assert float((bn.bias.grad.double().cpu() - ref.bias.grad).abs().max()) <= TOL * sc(ref.bias.grad)
+    if res:
+        assert float((r.grad.double().cpu() - rr.grad).abs().max()) <= TOL
+    assert float((bn.running_mean.double().cpu() - ref.running_mean).abs().max()) <= 1e-5
+    assert float((bn.running_var.double().cpu() - ref.running_var).abs().max()) <= 1e-5
+    assert int(bn.num_batches_tracked) == 1
