@@ -121,8 +121,20 @@ class _Backbone8xBase(nn.Module):
                                 conv_type="spconv")
             setattr(self, f"conv{s}" + sfx, sp.SparseSequential(down, *self._stage_blocks(nf[s - 1], norm_fn, k(f"{sub}{s}"), n)))
 
+    SORT_INPUT = True   # process the tower in ascending linear-key order (see _run_tower)
+
     def _run_tower(self, sfx, feats, coords, batch_size, with_out):
-        x = sp.SparseConvTensor(feats, coords.int() if coords.dtype != torch.int32 else coords, self.sparse_shape, batch_size)
+        coords = coords.int() if coords.dtype != torch.int32 else coords
+        if self.SORT_INPUT and coords.shape[0] > 0:
+            # The voxelizer emits rows in first-appearance (i.e. shuffled) order.  A sparse tensor is a set, so the
+            # tower may visit it in any order: ascending ((b*D+z)*H+y)*W+x -- the order every strided conv already
+            # produces -- makes each 128-row tile spatially compact, so gathers hit L2/L1 and empty taps are skipped.
+            d, h, w = self.sparse_shape
+            c64 = coords.long()
+            key = ((c64[:, 0] * d + c64[:, 1]) * h + c64[:, 2]) * w + c64[:, 3]
+            perm = torch.argsort(key)
+            feats, coords = feats.index_select(0, perm), coords.index_select(0, perm).contiguous()
+        x = sp.SparseConvTensor(feats, coords, self.sparse_shape, batch_size)
         x = getattr(self, "conv_input" + sfx)(x)
         c1 = getattr(self, "conv1" + sfx)(x)
         c2 = getattr(self, "conv2" + sfx)(c1)
