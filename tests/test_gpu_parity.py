@@ -146,9 +146,10 @@ def test_gather_gemm_fwd_bwd(oracle, cuda, cin, cout, kind):
         dxg = ops.gather_gemm(ddy, ops.weight_transpose(dw_, flip_taps=False), dev(tb, cuda), algo=ops.ALGO_SIMT)
     assert np.abs(dxg.cpu().numpy() - gx).max() <= TOL
     scale_w = max(1.0, np.abs(gw).max())
-    algos = [ops.ALGO_SIMT] + ([ops.ALGO_TCGEN05] if cin >= 16 and cout >= 16 else [])
+    algos = [ops.ALGO_SIMT] + ([ops.ALGO_TCGEN05] if cin >= 8 and cin % 8 == 0 and cout >= 8 else [])
+    nbr_t = nbr.t().contiguous()
     for algo in algos:                                             # fp32 SIMT and tcgen05 (3xTF32, MN-major) weight gradients
-        dwg, dbg = ops.gather_wgrad(dx_, ddy, nbr, want_bias=True, algo=algo)
+        dwg, dbg = ops.gather_wgrad(dx_, ddy, nbr_t, want_bias=True, algo=algo, tap_major=True)
         assert np.abs(dwg.cpu().numpy() - gw).max() <= TOL * scale_w, algo
         assert np.abs(dbg.cpu().numpy() - gb).max() <= TOL * max(1.0, np.abs(gb).max())
     if cin % 8 == 0 and cout in (16, 32, 64, 128, 256):            # tcgen05 forward / input-gradient

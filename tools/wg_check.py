@@ -18,7 +18,8 @@ for (m_in, m_out, cin, cout, K, dens) in cases:
     if K > 5:
         nbr[:, 5] = -1
     ref, _ = ops.gather_wgrad(x, dy, nbr, algo=ops.ALGO_SIMT)
-    got, _ = ops.gather_wgrad(x, dy, nbr, algo=ops.ALGO_TCGEN05)
+    nbr_t = nbr.t().contiguous()
+    got, _ = ops.gather_wgrad(x, dy, nbr.t().contiguous(), algo=ops.ALGO_TCGEN05, tap_major=True)
     nbr_t = nbr.t().contiguous()
     got_t, _ = ops.gather_wgrad(x, dy, nbr_t, algo=ops.ALGO_TCGEN05, tap_major=True)
     ref_t, _ = ops.gather_wgrad(x, dy, nbr_t, algo=ops.ALGO_SIMT, tap_major=True)
@@ -34,7 +35,7 @@ for (m_in, m_out, cin, cout, K, dens) in cases:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(3):
-            ops.gather_wgrad(x, dy, nbr, algo=algo)
+            ops.gather_wgrad(x, dy, nbr_t, algo=algo, tap_major=True)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 3
         P = int((nbr >= 0).sum())
