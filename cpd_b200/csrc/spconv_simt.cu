@@ -16,9 +16,14 @@ int32_t gather_gemm_tc(const float *x, int64_t m_in, int32_t cin, const float *w
                        cudaStream_t stream);
 size_t gather_gemm_tc_workspace(int64_t m_out, int32_t cin, int32_t K, int32_t cout);
 bool gather_gemm_tc_supported(int32_t cin, int32_t K, int32_t cout);
-bool gather_wgrad_tc_supported(int32_t cin, int32_t K, int32_t cout);
-int32_t gather_wgrad_tc(const float *x, int32_t cin, const float *dy, int64_t m_out, int32_t cout, const int32_t *nbr_t,
-                        int32_t K, float *dw, cudaStream_t stream);
+// two tcgen05 weight-gradient kernels: row-stationary with taps along N (wgrad_tc.cu, best for C_in <= 32, needs the
+// tap-major table) and per-tap pair lists (wgrad_pairs_tc.cu, best for C_in >= 64)
+bool gather_wgrad_rows_supported(int32_t cin, int32_t K, int32_t cout);
+int32_t gather_wgrad_rows_tc(const float *x, int32_t cin, const float *dy, int64_t m_out, int32_t cout, const int32_t *nbr_t,
+                             int32_t K, float *dw, cudaStream_t stream);
+bool gather_wgrad_pairs_supported(int32_t cin, int32_t K, int32_t cout);
+int32_t gather_wgrad_pairs_tc(const float *x, int32_t cin, const float *dy, int64_t m_out, int32_t cout, const int32_t *nbr,
+                              int32_t K, int32_t tap_major, float *dw, cudaStream_t stream);
 
 namespace {
 
@@ -369,17 +374,21 @@ extern "C" int32_t cpd_gather_wgrad(const float *x, int64_t m_in, int32_t cin, c
     CPD_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)cout * K * cin, stream));
     if (dbias) CPD_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)cout, stream));
     if (m_out == 0) return CPD_OK;
+    const bool tap_major_ok = nbr_tap_major || K == 1;
+    const bool rows_ok = gather_wgrad_rows_supported(cin, K, cout) && tap_major_ok;
+    const bool pairs_ok = gather_wgrad_pairs_supported(cin, K, cout);
+    static const int rows_max_cin = getenv("CPD_WGRAD_ROWS_MAX_CIN") ? atoi(getenv("CPD_WGRAD_ROWS_MAX_CIN")) : 32;   // tuning knob
     bool tc = false;
-    const bool tap_major_ok = nbr_tap_major || K == 1;      // the tcgen05 kernel scans the tap-major table
     if (algo == CPD_ALGO_TCGEN05) {
-        CPD_REQUIRE(gather_wgrad_tc_supported(cin, K, cout) && tap_major_ok, CPD_ERR_UNSUPPORTED,
-                    "cpd_gather_wgrad: tcgen05 path needs a tap-major table, cin in {8,16,32,64,128,256k}, cout %% 4 == 0");
+        CPD_REQUIRE(rows_ok || pairs_ok, CPD_ERR_UNSUPPORTED, "cpd_gather_wgrad: tcgen05 path needs cin, cout >= 8 and multiples of 4");
         tc = true;
     } else if (algo == CPD_ALGO_AUTO) {
-        tc = gather_wgrad_tc_supported(cin, K, cout) && tap_major_ok;
+        tc = rows_ok || pairs_ok;
     }
     if (tc) {
-        int32_t st = gather_wgrad_tc(x, cin, dy, m_out, cout, nbr, K, dw, stream);
+        int32_t st;
+        if (rows_ok && (cin <= rows_max_cin || !pairs_ok)) st = gather_wgrad_rows_tc(x, cin, dy, m_out, cout, nbr, K, dw, stream);
+        else st = gather_wgrad_pairs_tc(x, cin, dy, m_out, cout, nbr, K, nbr_tap_major, dw, stream);
         if (st) return st;
     }
     const int co_tiles = (int)div_up(cout, 64), ci_tiles = (int)div_up(cin, 64);

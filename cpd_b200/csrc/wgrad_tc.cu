@@ -74,7 +74,7 @@ struct WgArgs {
 };
 
 template <int BN, int AM>
-__global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_tc_kernel(WgArgs a)
+__global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a)
 {
     constexpr int STAGES = w_stages(BN, AM), STAGE = w_stage_bytes(BN, AM);
     constexpr int A_BYTES = KB * AM * 4, B_BYTES = KB * BN * 4;
@@ -287,10 +287,10 @@ int32_t launch_wg(const WgArgs &a, dim3 grid, cudaStream_t stream)
     static_assert(wg_smem<BN, AM>() <= 227 * 1024, "shared memory budget");
     static bool configured = false;
     if (!configured) {
-        CPD_CUDA(cudaFuncSetAttribute(gather_wgrad_tc_kernel<BN, AM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem<BN, AM>()));
+        CPD_CUDA(cudaFuncSetAttribute(gather_wgrad_rows_kernel<BN, AM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem<BN, AM>()));
         configured = true;
     }
-    gather_wgrad_tc_kernel<BN, AM><<<grid, NTHREADS, wg_smem<BN, AM>(), stream>>>(a);
+    gather_wgrad_rows_kernel<BN, AM><<<grid, NTHREADS, wg_smem<BN, AM>(), stream>>>(a);
     count_launch();
     return launch_status("cpd_gather_wgrad[tcgen05]");
 }
@@ -305,7 +305,7 @@ int32_t launch_wg_am(int am, const WgArgs &a, dim3 grid, cudaStream_t stream)
 
 }  // namespace
 
-bool gather_wgrad_tc_supported(int32_t cin, int32_t K, int32_t cout)
+bool gather_wgrad_rows_supported(int32_t cin, int32_t K, int32_t cout)
 {
     // cin must tile N: either a divisor-friendly small width (cin | 256 or cin | 128) or a multiple of 256
     const bool cin_ok = cin >= 8 && cin % 4 == 0 && ((cin <= 256 && 256 % cin == 0) || cin % 256 == 0);
@@ -313,10 +313,10 @@ bool gather_wgrad_tc_supported(int32_t cin, int32_t K, int32_t cout)
 }
 
 // dw must be zeroed by the caller (split-K reductions).  nbr_t: tap-major (K, m_out) table.
-int32_t gather_wgrad_tc(const float *x, int32_t cin, const float *dy, int64_t m_out, int32_t cout, const int32_t *nbr_t,
+int32_t gather_wgrad_rows_tc(const float *x, int32_t cin, const float *dy, int64_t m_out, int32_t cout, const int32_t *nbr_t,
                         int32_t K, float *dw, cudaStream_t stream)
 {
-    CPD_REQUIRE(gather_wgrad_tc_supported(cin, K, cout), CPD_ERR_UNSUPPORTED, "tcgen05 wgrad: unsupported shape");
+    CPD_REQUIRE(gather_wgrad_rows_supported(cin, K, cout), CPD_ERR_UNSUPPORTED, "tcgen05 wgrad: unsupported shape");
     CPD_REQUIRE((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) == 0, CPD_ERR_MISALIGNED, "tcgen05 wgrad: pointers must be 16-byte aligned");
     // N tile: 256 when the taps of a group (or cin itself) fill it, else 128
     const int bn = (cin >= 256 || (long long)K * cin > 128) ? 256 : 128;
