@@ -7,17 +7,17 @@
 // cpd/models/dense_heads/center_head.py:11-45,73-80).
 //
 // One CTA = 128 output rows x all BN = C_out columns, accumulator in TMEM (BN columns).
-//   warps 0-3  producers: gather A rows (x[nbr[o,k]], 128 B per row per k-block) and the
+//   warps 0-7  producers: gather A rows (x[nbr[o,k]], 128 B per row per k-block) and the
 //              W[:,k,c0:c0+32] slab straight from global/L2 with 16-byte loads, split every
 //              fp32 into tf32 hi + lo parts in registers and store both into shared memory in
 //              the canonical K-major SWIZZLE_128B layout that UMMA descriptors address
 //              (gathered rows are not TMA-tileable; the split has to pass through registers
 //              anyway).  fence.proxy.async + mbarrier arrive hand the stage to the MMA warp.
 //              Taps for which no row of the tile has a neighbour are skipped altogether.
-//   warp 4     allocates TMEM, then one elected lane issues per k-block 4 x 3
+//   warp 8     allocates TMEM, then one elected lane issues per k-block 4 x 3
 //              tcgen05.mma.cta_group::1.kind::tf32 (A_hi.B_hi + A_lo.B_hi + A_hi.B_lo, M=128,
 //              N=BN, K=8) and tcgen05.commit's the stage back to the producers.
-//   warps 0-3  epilogue: tcgen05.ld the accumulator (lane = row), + bias, stage through shared
+//   warps 0-7  epilogue: tcgen05.ld the accumulator (lane = row), + bias, stage through shared
 //              memory (padded rows, conflict-free), then coalesced float4 stores with the folded
 //              BatchNorm affine / residual / ReLU applied on the way out and per-channel
 //              sum / sum-of-squares taken from the staged tile.
@@ -32,8 +32,10 @@ using namespace tc;
 
 constexpr int BM = 128;       // UMMA M
 constexpr int BK = 32;        // fp32 per k-block = 128 bytes = one swizzle row
-constexpr int NPROD = 128;    // producer / epilogue threads (warps 0..3)
-constexpr int NTHREADS = 160; // + MMA warp
+constexpr int NPW = 8;             // producer / epilogue warps (two per SM sub-partition, so their issue stalls overlap)
+constexpr int NPROD = NPW * 32;
+constexpr int NTHREADS = NPROD + 32;   // + MMA warp (warp NPW)
+constexpr int RSTEP = NPROD / 8;   // row stride between the chunks one producer thread owns (8 x 16 B chunks per row)
 constexpr int MAX_TAPS = 32;
 
 __host__ __device__ constexpr int stages_for(int bn) { return bn >= 256 ? 2 : bn >= 128 ? 3 : 2; }
@@ -101,9 +103,9 @@ __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kern
     const int n0 = blockIdx.y * BN;                    // output-channel tile (cout > 256 is split over grid.y)
 
     if (tid == 0) misc[1] = 0u;
-    if (warp == 4) {
+    if (warp == NPW) {
         if (lane == 0) {
-            for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, NPROD); mbar_init(empty0 + 8 * s, 1); }
+            for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, NPW); mbar_init(empty0 + 8 * s, 1); }
             mbar_init(accum_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kern
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     __syncthreads();
-    if (warp < 4) {   // neighbour tile -> smem, and the set of taps that have any work in this tile
+    if (tid < BM) {   // neighbour tile -> smem, and the set of taps that have any work in this tile
         const long long row = row0 + tid;
         uint32_t mine = 0u;
         for (int k = 0; k < a.K; ++k) {
@@ -131,63 +133,60 @@ __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kern
     const int kblocks = (a.cin + BK - 1) / BK;
     const int n_iters = __popc(tap_mask) * kblocks;
     if (tid < a.K && ((tap_mask >> tid) & 1u)) misc[2 + __popc(tap_mask & ((1u << tid) - 1u))] = (uint32_t)tid;   // compact tap list
-    asm volatile("bar.sync 2, 160;" ::: "memory");
+    asm volatile("bar.sync 2, %0;" ::"n"(NTHREADS) : "memory");
 
-    if (warp < 4) {
+    if (warp < NPW) {
         // ================= producers =================
         // Software-pipelined: the gather loads of k-block it+1 are in flight while k-block it is
-        // split and stored (register double buffering; single-buffered for BN=256 to stay under 255 regs).
-        const int c = tid & 7, r_base = tid >> 3;   // 16-byte chunk, first row (rows r_base + 16 j)
-        uint32_t soff[BM / 16];                     // swizzled byte offsets of this thread's chunks (loop invariant;
-#pragma unroll                                      //  the B tile uses the first BN/16 of them)
-        for (int j = 0; j < BM / 16; ++j) soff[j] = swz(r_base + 16 * j, c);
-        auto load = [&](int it, float4(&av)[BM / 16], float4(&bv)[BN / 16]) {
+        // split and stored (register double buffering).
+        constexpr int A_V = BM / RSTEP, B_V = (BN + RSTEP - 1) / RSTEP;   // 16-byte chunks per thread per k-block
+        const int c = tid & 7, r_base = tid >> 3;   // 16-byte chunk, first row (rows r_base + RSTEP j)
+        const bool b_own = BN >= RSTEP || r_base < BN;
+        uint32_t soff[A_V];                         // swizzled byte offsets of this thread's chunks (loop invariant;
+#pragma unroll                                      //  the B tile reuses them, 128 rows = 16 KB apart)
+        for (int j = 0; j < A_V; ++j) soff[j] = swz(r_base + RSTEP * j, c);
+        auto load = [&](int it, float4(&av)[A_V], float4(&bv)[B_V]) {
             const int k = (int)misc[2 + it / kblocks];               // it/kblocks-th active tap
             const int col = (it % kblocks) * BK + c * 4;
             const bool col_ok = col < a.cin;
 #pragma unroll
-            for (int j = 0; j < BM / 16; ++j) {
-                const int32_t idx = nbr_s[k * BM + r_base + 16 * j];
+            for (int j = 0; j < A_V; ++j) {
+                const int32_t idx = nbr_s[k * BM + r_base + RSTEP * j];
                 av[j] = (idx >= 0 && col_ok) ? __ldg(reinterpret_cast<const float4 *>(a.x + (size_t)idx * a.cin + col))
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int j = 0; j < BN / 16; ++j) {
-                const int n = n0 + r_base + 16 * j;
-                bv[j] = col_ok ? __ldg(reinterpret_cast<const float4 *>(a.w + ((size_t)n * a.K + k) * a.cin + col))
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < B_V; ++j) {
+                const int n = n0 + r_base + RSTEP * j;
+                bv[j] = (col_ok && b_own) ? __ldg(reinterpret_cast<const float4 *>(a.w + ((size_t)n * a.K + k) * a.cin + col))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        auto store = [&](int it, const float4(&av)[BM / 16], const float4(&bv)[BN / 16]) {
+        auto store = [&](int it, const float4(&av)[A_V], const float4(&bv)[B_V]) {
             const int s = it % STAGES;
             mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
             uint8_t *st = tiles + s * STAGE;
 #pragma unroll
-            for (int j = 0; j < BM / 16; ++j) split_store(st, st + A_BYTES, soff[j], av[j]);
+            for (int j = 0; j < A_V; ++j) split_store(st, st + A_BYTES, soff[j], av[j]);
+            if (b_own) {
 #pragma unroll
-            for (int j = 0; j < BN / 16; ++j)      // rows r_base + 16 j; 128 rows = 16 KB of swizzled tile
-                split_store(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, soff[j & 7] + (uint32_t)(j >> 3) * 16384u, bv[j]);
-            fence_async_smem();
-            mbar_arrive(full0 + 8 * s);
-        };
-        if constexpr (BN <= 128) {
-            if (n_iters > 0) {
-                float4 a0[BM / 16], b0[BN / 16], a1[BM / 16], b1[BN / 16];
-                load(0, a0, b0);
-                for (int it = 0; it < n_iters; it += 2) {
-                    if (it + 1 < n_iters) load(it + 1, a1, b1);
-                    store(it, a0, b0);
-                    if (it + 1 < n_iters) {
-                        if (it + 2 < n_iters) load(it + 2, a0, b0);
-                        store(it + 1, a1, b1);
-                    }
-                }
+                for (int j = 0; j < B_V; ++j)      // rows r_base + RSTEP j; 128 rows = 16 KB of swizzled tile
+                    split_store(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, soff[j % A_V] + (uint32_t)(j / A_V) * 16384u, bv[j]);
             }
-        } else {
-            for (int it = 0; it < n_iters; ++it) {
-                float4 av[BM / 16], bv[BN / 16];
-                load(it, av, bv);
-                store(it, av, bv);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full0 + 8 * s);      // one arrival per producer warp
+        };
+        if (n_iters > 0) {
+            float4 a0[A_V], b0[B_V], a1[A_V], b1[B_V];
+            load(0, a0, b0);
+            for (int it = 0; it < n_iters; it += 2) {
+                if (it + 1 < n_iters) load(it + 1, a1, b1);
+                store(it, a0, b0);
+                if (it + 1 < n_iters) {
+                    if (it + 2 < n_iters) load(it + 2, a0, b0);
+                    store(it + 1, a1, b1);
+                }
             }
         }
         // ================= epilogue =================
@@ -196,16 +195,21 @@ __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kern
             mbar_wait(accum_bar, 0);
             tc_fence_after();
         }
-        const int my_row = warp * 32 + lane;
+        // warp w may read TMEM lanes 32*(w%4)..+31; the two warps sharing a lane quarter split the columns
+        const int my_row = (warp & 3) * 32 + lane;
         const int n_acc = n_iters == 0 ? 0 : (n_iters < NMAIN ? n_iters : NMAIN) + 1;   // mains in use + correction
+        constexpr int COLS_PER_GROUP = BN / (NPW / 4) >= 16 ? BN / (NPW / 4) : 16;
+        const int c_begin = (warp >> 2) * COLS_PER_GROUP;
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        for (int cc = 0; cc < COLS_PER_GROUP; cc += 16) {
+            const int c0 = c_begin + cc;
+            if (c0 >= BN) break;
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = 0.f;
             for (int acc = 0; acc < n_acc; ++acc) {
                 const int slot = acc == n_acc - 1 ? NMAIN : acc;                              // last one read = correction
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(slot * BN + c0);
+                const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(slot * BN + c0);
                 uint32_t u[16];
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -229,7 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kern
             }
         }
         tc_fence_before();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
         if (a.stats && tid < BN) {   // training-mode BatchNorm statistics of the pre-affine output
             float s = 0.f, q = 0.f;
             const int rows = (int)min((long long)BM, a.m_out - row0);
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kern
             *reinterpret_cast<float4 *>(a.y + row * a.cout + cv) = o;
         }
     } else {
-        // ================= MMA issuer (warp 4) =================
+        // ================= MMA issuer (warp NPW) =================
         for (int it = 0; it < n_iters; ++it) {
             const int s = it % STAGES;
             mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
@@ -289,7 +293,7 @@ __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kern
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == NPW) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols(BN)));
     }
