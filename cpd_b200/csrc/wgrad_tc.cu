@@ -13,12 +13,12 @@
 // tf32 MN-major operands have exactly one legal shared-memory layout, SWIZZLE_128B_BASE32B.
 //
 // One CTA = (tap group, slice of the output rows, <=128-wide cout tile AM, BN-wide (tap,cin) tile):
-//   warps 0-3  per 32-row k-block: load the dY rows (A, contiguous) and gather the X rows of each tap
+//   warps 0-7  per 32-row k-block: load the dY rows (A, contiguous) and gather the X rows of each tap
 //              of the group (B; neighbour indices come from a shared-memory copy of the tap-major
 //              table, prefetched one 128-row window ahead), split into tf32 hi/lo, store swizzled;
-//   warp 4     issues 4 x 3 tcgen05.mma kind::tf32 per k-block into a main and a correction TMEM
+//   warp 8     issues 4 x 3 tcgen05.mma kind::tf32 per k-block into a main and a correction TMEM
 //              accumulator (A_hi.B_hi | A_lo.B_hi + A_hi.B_lo, see spconv_tc.cu);
-//   warps 0-3  finally tcgen05.ld both accumulators and add them into dW with vector fp32 reductions
+//   warps 0-7  finally tcgen05.ld both accumulators and add them into dW with vector fp32 reductions
 //              (split-K over row slices; dW is zeroed by the host wrapper first).
 // For cout tiles narrower than 128 only AM = 32/64 columns of the A tile exist in shared memory: the
 // descriptor's 32-column blocks beyond AM alias whatever follows, which only pollutes accumulator
@@ -31,8 +31,9 @@ using namespace tc;
 
 constexpr int KB = 32;           // rows per k-block (4 MMA K-steps of 8)
 constexpr int WINR = 128;        // rows per neighbour-table window (4 k-blocks)
-constexpr int NPROD = 128;
-constexpr int NTHREADS = 160;
+constexpr int NPW = 8;            // producer / epilogue warps
+constexpr int NPROD = NPW * 32;
+constexpr int NTHREADS = NPROD + 32;
 constexpr uint32_t END_MARK = 0xffffffffu;
 constexpr int MAX_T = 32;        // taps per group (cin = 8 -> 32 taps in N = 256)
 constexpr int MAX_STEPS_PER_CTA = 512;   // k8 steps accumulated in one TMEM accumulator (bounds the truncation bias)
@@ -40,7 +41,7 @@ constexpr int MAX_STEPS_PER_CTA = 512;   // k8 steps accumulated in one TMEM acc
 __host__ __device__ constexpr int w_stage_bytes(int bn, int am) { return 2 * KB * am * 4 + 2 * KB * bn * 4; }
 __host__ __device__ constexpr int w_stages(int bn, int am)
 {
-    int s = (176 * 1024) / w_stage_bytes(bn, am);
+    int s = (160 * 1024) / w_stage_bytes(bn, am);
     return s > 4 ? 4 : (s < 2 ? 2 : s);
 }
 __host__ __device__ constexpr int w_tmem_cols(int bn) { return 2 * bn < 32 ? 32 : 2 * bn; }   // main + correction
@@ -87,8 +88,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    int32_t *nbr_w = reinterpret_cast<int32_t *>(tiles + STAGES * STAGE);       // [MAX_T][WINR]  (also the over-read slack)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(nbr_w + MAX_T * WINR);        // full[S], empty[S], accum
+    int32_t *nbr_w = reinterpret_cast<int32_t *>(tiles + STAGES * STAGE);       // [2][MAX_T][WINR]  (also the over-read slack)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(nbr_w + 2 * MAX_T * WINR);    // full[S], empty[S], accum
     uint32_t *info = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);       // [S] k8 steps valid in the stage / END
     uint32_t *misc = info + STAGES;                                             // [0] tmem base
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum_bar = smem_u32(bars + 2 * STAGES);
@@ -101,9 +102,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
     const long long r_end = min(r_begin + (long long)a.rows_per_cta, a.m_out);
     const int n_blocks = (int)((r_end - r_begin + KB - 1) / KB);
 
-    if (warp == 4) {
+    if (warp == NPW) {
         if (lane == 0) {
-            for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, NPROD); mbar_init(empty0 + 8 * s, 1); }
+            for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, NPW); mbar_init(empty0 + 8 * s, 1); }
             mbar_init(accum_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
     tc_fence_after();
     const uint32_t tmem_base = misc[0];
 
-    if (warp < 4) {
+    if (warp < NPW) {
         // Zero all operand stages once: columns beyond cout / (T*cin) are never written again.
         for (int e = tid; e < STAGES * STAGE / 16; e += NPROD) reinterpret_cast<float4 *>(tiles)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
         // loop-invariant mapping.  A: e = tid + 128 j over 32 x (AM/4) chunks.
@@ -137,9 +138,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
         uint32_t b_off[B_V];
 #pragma unroll
         for (int j = 0; j < B_V; ++j) b_off[j] = swz_mn(b_row0 + B_RSTEP * j, b_c4);
-        const int32_t *my_nbr = nbr_w + b_t * WINR + b_row0;
+        const int my_nbr_off = b_t * WINR + b_row0;
 
-        // ---- neighbour-table windows: T x 128 entries, prefetched into registers one window ahead ----
+        // ---- neighbour-table windows (T x 128 entries): fetched into registers two windows ahead, published into
+        //      a double-buffered shared-memory copy one window ahead of the gathers that read it ----
         constexpr int NW = (MAX_T * WINR) / NPROD;      // table entries per thread per window (upper bound)
         int32_t nreg[NW];
         auto fetch_window = [&](long long w0) {
@@ -150,58 +152,81 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
                 nreg[q] = (t < T && o < r_end) ? __ldg(a.nbr_t + (long long)(tap0 + t) * a.m_out + o) : -1;
             }
         };
-        auto publish_window = [&]() {
+        auto publish_window = [&](int buf) {
 #pragma unroll
             for (int q = 0; q < NW; ++q) {
                 const int e = tid + NPROD * q;
-                if (e / WINR < T) nbr_w[e] = nreg[q];
+                if (e / WINR < T) nbr_w[buf * MAX_T * WINR + e] = nreg[q];
             }
         };
-        fetch_window(r_begin);
-        asm volatile("bar.sync 1, 128;" ::: "memory");     // tiles zeroed
         int it = 0;
-        for (long long w0 = r_begin; w0 < r_end; w0 += WINR) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");     // previous window fully consumed
-            publish_window();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (w0 + WINR < r_end) fetch_window(w0 + WINR);    // in flight while this window is processed
-            const int nb = (int)min((long long)(WINR / KB), (r_end - w0 + KB - 1) / KB);
-            for (int kb = 0; kb < nb; ++kb, ++it) {
-                const long long r0 = w0 + kb * KB;
-                const int nvalid = (int)min((long long)KB, r_end - r0);
-                float4 av[A_V], bv[B_V];
+        auto load = [&](int blk, float4(&av)[A_V], float4(&bv)[B_V]) {
+            const long long r0 = r_begin + (long long)blk * KB;
+            const int nvalid = (int)min((long long)KB, r_end - r0);
+            const int32_t *tab = nbr_w + ((blk / (WINR / KB)) & 1) * MAX_T * WINR + my_nbr_off + (blk % (WINR / KB)) * KB;
 #pragma unroll
-                for (int j = 0; j < A_V; ++j)
-                    av[j] = (a_live[j] && a_row[j] < nvalid) ? __ldg(reinterpret_cast<const float4 *>(a.dy + (r0 + a_row[j]) * a.cout + a_col[j]))
-                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < A_V; ++j)
+                av[j] = (a_live[j] && a_row[j] < nvalid) ? __ldg(reinterpret_cast<const float4 *>(a.dy + (r0 + a_row[j]) * a.cout + a_col[j]))
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < B_V; ++j) {
+                const int32_t idx = b_live ? tab[B_RSTEP * j] : -1;
+                bv[j] = idx >= 0 ? __ldg(reinterpret_cast<const float4 *>(a.x + (size_t)idx * a.cin + b_ci)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto store = [&](int blk, const float4(&av)[A_V], const float4(&bv)[B_V]) {
+            const int s = it % STAGES;
+            mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
+            uint8_t *st = tiles + s * STAGE;
+#pragma unroll
+            for (int j = 0; j < A_V; ++j) {
+                if (!a_live[j]) continue;
+                float4 h, l;
+                split4(av[j], h, l);
+                *reinterpret_cast<float4 *>(st + a_off[j]) = h;
+                *reinterpret_cast<float4 *>(st + A_BYTES + a_off[j]) = l;
+            }
+            if (b_live) {
 #pragma unroll
                 for (int j = 0; j < B_V; ++j) {
-                    const int32_t idx = b_live ? my_nbr[kb * KB + B_RSTEP * j] : -1;
-                    bv[j] = idx >= 0 ? __ldg(reinterpret_cast<const float4 *>(a.x + (size_t)idx * a.cin + b_ci)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                const int s = it % STAGES;
-                mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
-                uint8_t *st = tiles + s * STAGE;
-#pragma unroll
-                for (int j = 0; j < A_V; ++j) {
-                    if (!a_live[j]) continue;
                     float4 h, l;
-                    split4(av[j], h, l);
-                    *reinterpret_cast<float4 *>(st + a_off[j]) = h;
-                    *reinterpret_cast<float4 *>(st + A_BYTES + a_off[j]) = l;
+                    split4(bv[j], h, l);
+                    *reinterpret_cast<float4 *>(st + 2 * A_BYTES + b_off[j]) = h;
+                    *reinterpret_cast<float4 *>(st + 2 * A_BYTES + B_BYTES + b_off[j]) = l;
                 }
-                if (b_live) {
-#pragma unroll
-                    for (int j = 0; j < B_V; ++j) {
-                        float4 h, l;
-                        split4(bv[j], h, l);
-                        *reinterpret_cast<float4 *>(st + 2 * A_BYTES + b_off[j]) = h;
-                        *reinterpret_cast<float4 *>(st + 2 * A_BYTES + B_BYTES + b_off[j]) = l;
-                    }
+            }
+            const int nvalid = (int)min((long long)KB, r_end - (r_begin + (long long)blk * KB));
+            if (tid == 0) info[s] = (uint32_t)((nvalid + 7) / 8);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full0 + 8 * s);      // one arrival per producer warp
+            ++it;
+        };
+        // before block `blk` is LOADED its window's table must be published; windows are 4 blocks long
+        auto prepare = [&](int blk) {
+            if (blk % (WINR / KB) != 0 || blk >= n_blocks) return;
+            const int w = blk / (WINR / KB);
+            asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");   // buffer (w & 1) no longer read (window w-2 is long done)
+            publish_window(w & 1);
+            asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
+            const long long next = r_begin + (long long)(w + 1) * WINR;
+            if (next < r_end) fetch_window(next);
+        };
+        fetch_window(r_begin);
+        asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");     // tiles zeroed
+        if (n_blocks > 0) {
+            float4 a0[A_V], b0v[B_V], a1[A_V], b1v[B_V];
+            prepare(0);
+            load(0, a0, b0v);
+            for (int blk = 0; blk < n_blocks; blk += 2) {
+                prepare(blk + 1);
+                if (blk + 1 < n_blocks) load(blk + 1, a1, b1v);
+                store(blk, a0, b0v);
+                if (blk + 1 < n_blocks) {
+                    prepare(blk + 2);
+                    if (blk + 2 < n_blocks) load(blk + 2, a0, b0v);
+                    store(blk + 1, a1, b1v);
                 }
-                if (tid == 0) info[s] = (uint32_t)((nvalid + 7) / 8);
-                fence_async_smem();
-                mbar_arrive(full0 + 8 * s);
             }
         }
         // ---- end marker, then epilogue ----
@@ -214,13 +239,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
         if (n_blocks > 0) {
             mbar_wait(accum_bar, 0);
             tc_fence_after();
-            const int co = co0 + warp * 32 + lane;
-            if (warp * 32 < AM) {                       // accumulator lanes >= AM hold aliased garbage
+            const int co = co0 + (warp & 3) * 32 + lane;      // warps w and w+4 share TMEM lanes and split the columns
+            if ((warp & 3) * 32 < AM) {                       // accumulator lanes >= AM hold aliased garbage
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 16) {
+                for (int c0 = (warp >> 2) * (BN / 2); c0 < ((warp >> 2) + 1) * (BN / 2); c0 += 16) {
                     uint32_t u[16], v[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, u);
-                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(BN + c0), v);
+                    tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, u);
+                    tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(BN + c0), v);
                     if (co < a.cout) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -268,7 +293,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == NPW) {
         tc_fence_after();
         tmem_dealloc(tmem_base, w_tmem_cols(BN));
     }
@@ -277,7 +302,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
 template <int BN, int AM>
 constexpr size_t wg_smem()
 {
-    return 1024 + (size_t)w_stages(BN, AM) * w_stage_bytes(BN, AM) + MAX_T * WINR * 4 + (2 * w_stages(BN, AM) + 1) * 8 +
+    return 1024 + (size_t)w_stages(BN, AM) * w_stage_bytes(BN, AM) + 2 * MAX_T * WINR * 4 + (2 * w_stages(BN, AM) + 1) * 8 +
            (w_stages(BN, AM) + 8) * 4;
 }
 
