@@ -234,7 +234,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
             const int s = it % STAGES;
             mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
             if (tid == 0) info[s] = END_MARK;
-            mbar_arrive(full0 + 8 * s);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full0 + 8 * s);      // barrier counts one arrival per producer warp
         }
         if (n_blocks > 0) {
             mbar_wait(accum_bar, 0);
