@@ -377,7 +377,7 @@ extern "C" int32_t cpd_gather_wgrad(const float *x, int64_t m_in, int32_t cin, c
     const bool tap_major_ok = nbr_tap_major || K == 1;
     const bool rows_ok = gather_wgrad_rows_supported(cin, K, cout) && tap_major_ok;
     const bool pairs_ok = gather_wgrad_pairs_supported(cin, K, cout);
-    static const int rows_max_cin = getenv("CPD_WGRAD_ROWS_MAX_CIN") ? atoi(getenv("CPD_WGRAD_ROWS_MAX_CIN")) : 32;   // tuning knob
+    static const int rows_max_cin = getenv("CPD_WGRAD_ROWS_MAX_CIN") ? atoi(getenv("CPD_WGRAD_ROWS_MAX_CIN")) : 1024;   // tuning knob
     bool tc = false;
     if (algo == CPD_ALGO_TCGEN05) {
         CPD_REQUIRE(rows_ok || pairs_ok, CPD_ERR_UNSUPPORTED, "cpd_gather_wgrad: tcgen05 path needs cin, cout >= 8 and multiples of 4");
@@ -387,7 +387,10 @@ extern "C" int32_t cpd_gather_wgrad(const float *x, int64_t m_in, int32_t cin, c
     }
     if (tc) {
         int32_t st;
-        if (rows_ok && (cin <= rows_max_cin || !pairs_ok)) st = gather_wgrad_rows_tc(x, cin, dy, m_out, cout, nbr, K, dw, stream);
+        // measured on B200 (tools/wg_check.py, tools/prof_layer.py): the row-stationary kernel wins everywhere except
+        // wide-in AND wide-out layers (256 -> 256), where the per-tap pair-list kernel's N = 256, M = 2 x 128 tiling is better
+        const bool prefer_rows = cin <= rows_max_cin && !(cin >= 256 && cout >= 256);
+        if (rows_ok && (prefer_rows || !pairs_ok)) st = gather_wgrad_rows_tc(x, cin, dy, m_out, cout, nbr, K, dw, stream);
         else st = gather_wgrad_pairs_tc(x, cin, dy, m_out, cout, nbr, K, nbr_tap_major, dw, stream);
         if (st) return st;
     }
