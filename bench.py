@@ -278,7 +278,14 @@ def run_ours(a):
         roof = dict(bound="hbm", achieved=top["bytes"] / top["ms"] / 1e6, peak=hbm, unit="GB/s")
     else:
         roof = dict(bound="tensor", achieved=top["flops"] / top["ms"] / 1e9, peak=tf32_peak, unit="TFLOP/s")
-    roof.update(frac=roof["achieved"] / roof["peak"], traffic=None, peak_source=f"{src} ({'HBM copy' if roof['bound'] == 'hbm' else 'bf16/2 = TF32 dense'})",
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    kname = f"{top_key[0]} {top_key[1]}->{top_key[2]} K={top_key[3]}"
+    if os.path.exists(tpath):
+        ent = json.load(open(tpath)).get(kname)
+        if ent:
+            traffic = ent["dram_bytes_per_launch"]
+    roof.update(frac=roof["achieved"] / roof["peak"], traffic=traffic, peak_source=f"{src} ({'HBM copy' if roof['bound'] == 'hbm' else 'bf16/2 = TF32 dense'})",
                 kernel=f"{top_key[0]} {top_key[1]}->{top_key[2]} K={top_key[3]}", launches=top["n"],
                 avg_launch_us=1e3 * top["ms"] / top["n"], share_of_step=top["ms"] / prof_ms,
                 gather_family_share_of_step=gg_ms / prof_ms,
