@@ -389,7 +389,8 @@ extern "C" int32_t cpd_gather_wgrad(const float *x, int64_t m_in, int32_t cin, c
         int32_t st;
         // measured on B200 (tools/wg_check.py, tools/prof_layer.py): the row-stationary kernel wins everywhere except
         // wide-in AND wide-out layers (256 -> 256), where the per-tap pair-list kernel's N = 256, M = 2 x 128 tiling is better
-        const bool prefer_rows = cin <= rows_max_cin && !(cin >= 256 && cout >= 256);
+        static const bool force_rows = getenv("CPD_WGRAD_FORCE_ROWS") != nullptr;                        // tuning knob
+        const bool prefer_rows = force_rows || (cin <= rows_max_cin && !(cin >= 256 && cout >= 256));
         if (rows_ok && (prefer_rows || !pairs_ok)) st = gather_wgrad_rows_tc(x, cin, dy, m_out, cout, nbr, K, dw, stream);
         else st = gather_wgrad_pairs_tc(x, cin, dy, m_out, cout, nbr, K, nbr_tap_major, dw, stream);
         if (st) return st;

@@ -1,29 +1,41 @@
 // tcgen05 gather-GEMM for sm_100a: y[o,:] = epi( sum_k W[:,k,:] x[nbr[o,k],:] ) with fp32-class
-// accuracy on the 5th-generation tensor cores (3xTF32 operand splitting).
+// accuracy on the 5th-generation tensor cores (bf16x3 operand splitting, fp32 accumulation in TMEM).
 //
 // Serves spconv.SubMConv3d / SparseConv3d forward + input-gradient (call sites
 // cpd/models/backbones_3d/spconv_backbone.py:17,20-21,108-115) and, through cpd_conv2d_table,
 // the dense BEV convolutions (cpd/models/backbones_2d/base_bev_backbone.py:31-59,
 // cpd/models/dense_heads/center_head.py:11-45,73-80).
 //
-// One CTA = 128 output rows x all BN = C_out columns, accumulator in TMEM (BN columns).
-//   warps 0-7  producers: gather A rows (x[nbr[o,k]], 128 B per row per k-block) and the
-//              W[:,k,c0:c0+32] slab straight from global/L2 with 16-byte loads, split every
-//              fp32 into tf32 hi + lo parts in registers and store both into shared memory in
-//              the canonical K-major SWIZZLE_128B layout that UMMA descriptors address
-//              (gathered rows are not TMA-tileable; the split has to pass through registers
-//              anyway).  fence.proxy.async + mbarrier arrive hand the stage to the MMA warp.
-//              Taps for which no row of the tile has a neighbour are skipped altogether.
+// The contraction index is the flattened (tap, channel) pair f = k * cin + c, cut into k-blocks of
+// 64 (= one 128-byte bf16 swizzle row): a 16- or 32-channel layer packs 4 or 2 taps into one
+// k-block, a 128-channel layer spends two k-blocks per tap.  W (cout, K, cin) is already contiguous
+// along f, so the B operand of k-block kb is simply W[:, 64 kb : 64 kb + 64].
+//
+// One CTA = 128 output rows x BN output channels, accumulators in TMEM.
+//   weight_split_kernel (one tiny launch before the GEMM): W -> bf16 hi / lo images stored in
+//              global memory ALREADY in the swizzled shared-memory tile layout, one contiguous
+//              [hi | lo] block of 2 * BN * 128 bytes per (k-block, cout tile).
+//   warp 9     per k-block ONE cp.async.bulk (TMA engine, no tensor map needed because the image
+//              is pre-swizzled) brings the B tile in, completing on the stage's full barrier.
+//   warps 0-7  producers: gather A rows (x[nbr[o,k]], 32 bytes of fp32 per thread per row) straight
+//              from global/L2, split every fp32 into bf16 hi + lo in registers and store both into
+//              shared memory in the canonical K-major SWIZZLE_128B layout that UMMA descriptors
+//              address (gathered rows are not TMA-tileable and the split has to pass through
+//              registers anyway).  fence.proxy.async + mbarrier arrive hand the stage over.
+//              k-blocks none of whose taps has a neighbour in the tile are skipped altogether.
 //   warp 8     allocates TMEM, then one elected lane issues per k-block 4 x 3
-//              tcgen05.mma.cta_group::1.kind::tf32 (A_hi.B_hi + A_lo.B_hi + A_hi.B_lo, M=128,
-//              N=BN, K=8) and tcgen05.commit's the stage back to the producers.
-//   warps 0-7  epilogue: tcgen05.ld the accumulator (lane = row), + bias, stage through shared
+//              tcgen05.mma.cta_group::1.kind::f16 (A_hi.B_hi + A_lo.B_hi + A_hi.B_lo, M=128,
+//              N=BN, K=16) and tcgen05.commit's the stage back.
+//   warps 0-7  epilogue: tcgen05.ld the accumulators (lane = row), + bias, stage through shared
 //              memory (padded rows, conflict-free), then coalesced float4 stores with the folded
 //              BatchNorm affine / residual / ReLU applied on the way out and per-channel
 //              sum / sum-of-squares taken from the staged tile.
 //
-// TF32 keeps 10 mantissa bits: a single-pass product would miss the 1e-4 parity bar
-// (SURVEY.md H4); hi = x & 0xffffe000, lo = x - hi (exact) restores ~2^-21 relative error.
+// Why bf16x3: one bf16 product keeps 8 mantissa bits, far from the 1e-4 parity bar;
+// hi = RN(x), lo = RN(x - hi) restores ~2^-17 relative error per product (measured ~1e-5 on the
+// layer outputs, tools/tc_check.py) and moves half the shared-memory bytes of a 3xTF32 split --
+// and shared-memory bandwidth (operand stores + UMMA operand reads), not the tensor pipe, is what
+// bounds a 3-product emulation at M = N = 128.
 #include "tc_common.cuh"
 
 namespace cpd {
@@ -31,21 +43,23 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128;       // UMMA M
-constexpr int BK = 32;        // fp32 per k-block = 128 bytes = one swizzle row
+constexpr int BKE = 64;       // bf16 elements per k-block = 128 bytes = one swizzle row
 constexpr int NPW = 8;             // producer / epilogue warps (two per SM sub-partition, so their issue stalls overlap)
 constexpr int NPROD = NPW * 32;
-constexpr int NTHREADS = NPROD + 32;   // + MMA warp (warp NPW)
+constexpr int NTHREADS = NPROD + 64;   // + MMA warp (warp NPW) + B-loader warp (warp NPW + 1)
 constexpr int RSTEP = NPROD / 8;   // row stride between the chunks one producer thread owns (8 x 16 B chunks per row)
+constexpr int A_V = BM / RSTEP;    // rows per producer thread per k-block
 constexpr int MAX_TAPS = 32;
+constexpr int MAX_KB = 512;        // k-blocks per tile (K * cin / 64)
 
 __host__ __device__ constexpr int stages_for(int bn) { return bn >= 256 ? 2 : bn >= 128 ? 3 : 2; }
 __host__ __device__ constexpr int ctas_per_sm(int bn) { return bn <= 64 ? 2 : 1; }
-__host__ __device__ constexpr int stage_bytes(int bn) { return 2 * BM * BK * 4 + 2 * bn * BK * 4; }
+__host__ __device__ constexpr int stage_bytes(int bn) { return 2 * BM * 128 + 2 * bn * 128; }
 // TMEM accumulators per tile: n_main(bn) "main" ones (A_hi.B_hi, k-blocks dealt round-robin) + 1
-// "correction" one (A_lo.B_hi + A_hi.B_lo, ~2^-11 of the main magnitude).  The tensor core
-// truncates when it adds into the fp32 accumulator; with thousands of adds into one accumulator
-// that bias reaches ~1e-4 (measured).  Spreading the adds over separate accumulators and summing
-// them in fp32 registers in the epilogue cuts it by 3 * n_main for free (TMEM columns are idle).
+// "correction" one (A_lo.B_hi + A_hi.B_lo, ~2^-9 of the main magnitude).  The tensor core
+// truncates when it adds into the fp32 accumulator; with hundreds of adds into one accumulator
+// that bias becomes visible at the 1e-4 level.  Spreading the adds over separate accumulators and
+// summing them in fp32 registers in the epilogue cuts it for free (TMEM columns are idle).
 __host__ __device__ constexpr int n_main(int bn) { return bn <= 128 ? 2 : 1; }
 __host__ __device__ constexpr int tmem_cols(int bn)
 {
@@ -60,52 +74,68 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // byte offset of 16-byte chunk c (0..7) of row r inside a [rows x 128 B] swizzled tile
-__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
-
-__device__ __forceinline__ void split_store(uint8_t *hi_tile, uint8_t *lo_tile, uint32_t off, float4 v)
-{
-    float4 h, l;
-    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
-    *reinterpret_cast<float4 *>(hi_tile + off) = h;
-    *reinterpret_cast<float4 *>(lo_tile + off) = l;
-}
+__host__ __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
 
 struct TcArgs {
-    const float *x, *w, *bias, *scale, *shift, *residual;
+    const float *x, *bias, *scale, *shift, *residual;
+    const uint8_t *wsplit;      // [k-block][cout tile][hi | lo][BN rows x 128 B, swizzled]
     const int32_t *nbr;
     float *stats, *y;
     long long m_out;
     int cin, K, cout, relu;
 };
 
+// W (cout, Kf) fp32 -> pre-swizzled bf16 hi / lo tile images.  One thread per 16-byte output chunk.
+__global__ void weight_split_kernel(const float *__restrict__ w, int cout, int Kf, int n_kb, int bn, uint8_t *__restrict__ out)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n_kb * cout * 8) return;
+    const int c = (int)(t & 7);
+    const int n = (int)((t >> 3) % cout), kb = (int)((t >> 3) / cout);
+    const int f = kb * BKE + c * 8;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (f < Kf) {                                   // Kf % 8 == 0: a chunk is entirely inside or outside
+        const float4 *p = reinterpret_cast<const float4 *>(w + (size_t)n * Kf + f);
+        v0 = __ldg(p); v1 = __ldg(p + 1);
+    }
+    uint4 h, l;
+    split8(v0, v1, h, l);
+    const int ntiles = cout / bn, nt = n / bn, nl = n % bn;
+    uint8_t *base = out + ((size_t)kb * ntiles + nt) * (size_t)(2 * bn * 128);
+    const uint32_t off = swz(nl, c);
+    *reinterpret_cast<uint4 *>(base + off) = h;
+    *reinterpret_cast<uint4 *>(base + (size_t)bn * 128 + off) = l;
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kernel(TcArgs a)
 {
     constexpr int STAGES = stages_for(BN);
     constexpr int NMAIN = n_main(BN);
-    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE = stage_bytes(BN);
+    constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE = stage_bytes(BN);
     constexpr int OUT_LD = BN + 4;   // padded staging row (floats): conflict-free 16-byte stores
     static_assert(BM * OUT_LD * 4 <= STAGES * STAGE, "epilogue staging must fit in the pipeline buffers");
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // fp32 accumulate (bit 4), bf16 A and B (bits 7, 10), K-major both, N >> 3, M >> 4
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     int32_t *nbr_s = reinterpret_cast<int32_t *>(tiles + STAGES * STAGE);          // [K][BM]
     uint64_t *bars = reinterpret_cast<uint64_t *>(nbr_s + a.K * BM);              // full[S], empty[S], accum
-    uint32_t *misc = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);         // [0] tmem base, [1] tap mask, [2..] active tap list
+    uint32_t *misc = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);         // [0] tmem base, [1] tap mask, [2] active k-blocks
+    uint16_t *kb_list = reinterpret_cast<uint16_t *>(misc + 4);                   // [n_kb] active k-block indices
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum_bar = smem_u32(bars + 2 * STAGES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long row0 = (long long)blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;                    // output-channel tile (cout > 256 is split over grid.y)
+    const int Kf = a.K * a.cin;
+    const int n_kb = (Kf + BKE - 1) / BKE;
 
     if (tid == 0) misc[1] = 0u;
     if (warp == NPW) {
         if (lane == 0) {
-            for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, NPW); mbar_init(empty0 + 8 * s, 1); }
+            for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, NPW + 1); mbar_init(empty0 + 8 * s, 1); }
             mbar_init(accum_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -129,63 +159,75 @@ __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kern
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = misc[0];
-    const uint32_t tap_mask = misc[1];
-    const int kblocks = (a.cin + BK - 1) / BK;
-    const int n_iters = __popc(tap_mask) * kblocks;
-    if (tid < a.K && ((tap_mask >> tid) & 1u)) misc[2 + __popc(tap_mask & ((1u << tid) - 1u))] = (uint32_t)tid;   // compact tap list
+    if (warp == 0) {   // ordered list of the k-blocks that touch at least one active tap
+        const uint32_t tap_mask = misc[1];
+        int cnt = 0;
+        for (int base = 0; base < n_kb; base += 32) {
+            const int kb = base + lane;
+            bool act = false;
+            if (kb < n_kb) {
+                const int t0 = (kb * BKE) / a.cin;
+                int t1 = (kb * BKE + BKE - 1) / a.cin;
+                if (t1 > a.K - 1) t1 = a.K - 1;
+                const uint32_t upto = t1 >= 31 ? 0xffffffffu : ((1u << (t1 + 1)) - 1u);
+                act = (tap_mask & upto & ~((1u << t0) - 1u)) != 0u;
+            }
+            const uint32_t b = __ballot_sync(0xffffffffu, act);
+            if (act) kb_list[cnt + __popc(b & ((1u << lane) - 1u))] = (uint16_t)kb;
+            cnt += __popc(b);
+        }
+        if (lane == 0) misc[2] = (uint32_t)cnt;
+    }
     asm volatile("bar.sync 2, %0;" ::"n"(NTHREADS) : "memory");
+    const int n_iters = (int)misc[2];
 
     if (warp < NPW) {
         // ================= producers =================
         // Software-pipelined: the gather loads of k-block it+1 are in flight while k-block it is
         // split and stored (register double buffering).
-        constexpr int A_V = BM / RSTEP, B_V = (BN + RSTEP - 1) / RSTEP;   // 16-byte chunks per thread per k-block
-        const int c = tid & 7, r_base = tid >> 3;   // 16-byte chunk, first row (rows r_base + RSTEP j)
-        const bool b_own = BN >= RSTEP || r_base < BN;
-        uint32_t soff[A_V];                         // swizzled byte offsets of this thread's chunks (loop invariant;
-#pragma unroll                                      //  the B tile reuses them, 128 rows = 16 KB apart)
+        const int c = tid & 7, r_base = tid >> 3;   // 16-byte smem chunk (8 channels), first row (rows r_base + RSTEP j)
+        uint32_t soff[A_V];                         // swizzled byte offsets of this thread's chunks (loop invariant)
+#pragma unroll
         for (int j = 0; j < A_V; ++j) soff[j] = swz(r_base + RSTEP * j, c);
-        auto load = [&](int it, float4(&av)[A_V], float4(&bv)[B_V]) {
-            const int k = (int)misc[2 + it / kblocks];               // it/kblocks-th active tap
-            const int col = (it % kblocks) * BK + c * 4;
-            const bool col_ok = col < a.cin;
+        auto load = [&](int it, float4(&av)[2 * A_V]) {
+            const int f = (int)kb_list[it] * BKE + c * 8;            // flattened (tap, channel) index of this thread's chunk
+            const int k = f / a.cin, ch = f - k * a.cin;
+            const int32_t *nb = nbr_s + (k < a.K ? k : 0) * BM + r_base;
 #pragma unroll
             for (int j = 0; j < A_V; ++j) {
-                const int32_t idx = nbr_s[k * BM + r_base + RSTEP * j];
-                av[j] = (idx >= 0 && col_ok) ? __ldg(reinterpret_cast<const float4 *>(a.x + (size_t)idx * a.cin + col))
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int j = 0; j < B_V; ++j) {
-                const int n = n0 + r_base + RSTEP * j;
-                bv[j] = (col_ok && b_own) ? __ldg(reinterpret_cast<const float4 *>(a.w + ((size_t)n * a.K + k) * a.cin + col))
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int32_t idx = k < a.K ? nb[RSTEP * j] : -1;
+                if (idx >= 0) {
+                    const float4 *p = reinterpret_cast<const float4 *>(a.x + (size_t)idx * a.cin + ch);
+                    av[2 * j] = __ldg(p); av[2 * j + 1] = __ldg(p + 1);
+                } else {
+                    av[2 * j] = make_float4(0.f, 0.f, 0.f, 0.f); av[2 * j + 1] = av[2 * j];
+                }
             }
         };
-        auto store = [&](int it, const float4(&av)[A_V], const float4(&bv)[B_V]) {
+        auto store = [&](int it, const float4(&av)[2 * A_V]) {
             const int s = it % STAGES;
             mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
             uint8_t *st = tiles + s * STAGE;
 #pragma unroll
-            for (int j = 0; j < A_V; ++j) split_store(st, st + A_BYTES, soff[j], av[j]);
-            if (b_own) {
-#pragma unroll
-                for (int j = 0; j < B_V; ++j)      // rows r_base + RSTEP j; 128 rows = 16 KB of swizzled tile
-                    split_store(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, soff[j % A_V] + (uint32_t)(j / A_V) * 16384u, bv[j]);
+            for (int j = 0; j < A_V; ++j) {
+                uint4 h, l;
+                split8(av[2 * j], av[2 * j + 1], h, l);
+                *reinterpret_cast<uint4 *>(st + soff[j]) = h;
+                *reinterpret_cast<uint4 *>(st + A_BYTES + soff[j]) = l;
             }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(full0 + 8 * s);      // one arrival per producer warp
         };
         if (n_iters > 0) {
-            float4 a0[A_V], b0[B_V], a1[A_V], b1[B_V];
-            load(0, a0, b0);
+            float4 a0[2 * A_V], a1[2 * A_V];
+            load(0, a0);
             for (int it = 0; it < n_iters; it += 2) {
-                if (it + 1 < n_iters) load(it + 1, a1, b1);
-                store(it, a0, b0);
+                if (it + 1 < n_iters) load(it + 1, a1);
+                store(it, a0);
                 if (it + 1 < n_iters) {
-                    if (it + 2 < n_iters) load(it + 2, a0, b0);
-                    store(it + 1, a1, b1);
+                    if (it + 2 < n_iters) load(it + 2, a0);
+                    store(it + 1, a1);
                 }
             }
         }
@@ -211,12 +253,7 @@ __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kern
                 const int slot = acc == n_acc - 1 ? NMAIN : acc;                              // last one read = correction
                 const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(slot * BN + c0);
                 uint32_t u[16];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                    : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
-                      "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tmem_ld16(taddr, u);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(u[j]);
             }
@@ -241,13 +278,6 @@ __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kern
             atomicAdd(a.stats + n0 + tid, s);
             atomicAdd(a.stats + a.cout + n0 + tid, q);
         }
-        if (BN > NPROD && a.stats && tid + NPROD < BN) {
-            float s = 0.f, q = 0.f;
-            const int rows = (int)min((long long)BM, a.m_out - row0);
-            for (int r = 0; r < rows; ++r) { float t = stage_out[r * OUT_LD + tid + NPROD]; s += t; q += t * t; }
-            atomicAdd(a.stats + n0 + tid + NPROD, s);
-            atomicAdd(a.stats + a.cout + n0 + tid + NPROD, q);
-        }
         constexpr int V_PER_ROW = BN / 4;
         for (int t = tid; t < BM * V_PER_ROW; t += NPROD) {
             const int r = t / V_PER_ROW, cl = (t % V_PER_ROW) * 4, cv = n0 + cl;
@@ -266,8 +296,8 @@ __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kern
             if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             *reinterpret_cast<float4 *>(a.y + row * a.cout + cv) = o;
         }
-    } else {
-        // ================= MMA issuer (warp NPW) =================
+    } else if (warp == NPW) {
+        // ================= MMA issuer =================
         for (int it = 0; it < n_iters; ++it) {
             const int s = it % STAGES;
             mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
@@ -276,14 +306,14 @@ __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kern
                 const uint32_t st = smem_u32(tiles + s * STAGE);
                 const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + A_BYTES);
                 const uint64_t b_hi = make_desc(st + 2 * A_BYTES), b_lo = make_desc(st + 2 * A_BYTES + B_BYTES);
-                const int kb = it % kblocks;
-                const int k8n = min(BK / 8, (a.cin - kb * BK + 7) / 8);
+                const int rem = Kf - (int)kb_list[it] * BKE;                  // contraction elements left from this k-block on
+                const int k16n = rem >= BKE ? BKE / 16 : (rem + 15) / 16;
                 const uint32_t d_main = tmem_base + (uint32_t)((it % NMAIN) * BN), d_corr = tmem_base + (uint32_t)(NMAIN * BN);
-                for (int k8 = 0; k8 < k8n; ++k8) {
-                    const uint64_t adv = (uint64_t)((k8 * 32) >> 4);   // +32 bytes along K inside the swizzle row
-                    umma_tf32(d_main, a_hi + adv, b_hi + adv, IDESC, (it >= NMAIN || k8) ? 1u : 0u);
-                    umma_tf32(d_corr, a_lo + adv, b_hi + adv, IDESC, (it | k8) ? 1u : 0u);
-                    umma_tf32(d_corr, a_hi + adv, b_lo + adv, IDESC, 1u);
+                for (int k16 = 0; k16 < k16n; ++k16) {
+                    const uint64_t adv = (uint64_t)((k16 * 32) >> 4);   // +32 bytes along K inside the swizzle row
+                    umma_bf16(d_main, a_hi + adv, b_hi + adv, IDESC, (it >= NMAIN || k16) ? 1u : 0u);
+                    umma_bf16(d_corr, a_lo + adv, b_hi + adv, IDESC, (it | k16) ? 1u : 0u);
+                    umma_bf16(d_corr, a_hi + adv, b_lo + adv, IDESC, 1u);
                 }
                 umma_commit(empty0 + 8 * s);            // frees the stage once these MMAs have read it
                 if (it == n_iters - 1) umma_commit(accum_bar);
@@ -291,6 +321,20 @@ __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kern
             __syncwarp();
         }
         tc_fence_before();
+    } else {
+        // ================= B loader: one bulk copy of the pre-swizzled [hi | lo] weight tile per k-block =================
+        const size_t tile_bytes = (size_t)(2 * B_BYTES);
+        const int ntiles = a.cout / BN;
+        for (int it = 0; it < n_iters; ++it) {
+            const int s = it % STAGES;
+            if (lane == 0) {
+                mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
+                const uint8_t *src = a.wsplit + ((size_t)kb_list[it] * ntiles + blockIdx.y) * tile_bytes;
+                mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)tile_bytes);
+                bulk_copy_g2s(smem_u32(tiles + s * STAGE + 2 * A_BYTES), src, (uint32_t)tile_bytes, full0 + 8 * s);
+            }
+            __syncwarp();
+        }
     }
     __syncthreads();
     if (warp == NPW) {
@@ -300,47 +344,64 @@ __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kern
 }
 
 template <int BN>
-size_t smem_bytes(int K) { return 1024 + (size_t)stages_for(BN) * stage_bytes(BN) + (size_t)K * BM * 4 + (2 * stages_for(BN) + 1) * 8 + (2 + MAX_TAPS) * 4; }
+size_t smem_bytes(int K, int n_kb)
+{
+    return 1024 + (size_t)stages_for(BN) * stage_bytes(BN) + (size_t)K * BM * 4 + (2 * stages_for(BN) + 1) * 8 + 4 * 4 +
+           (size_t)((n_kb + 7) / 8 * 8) * 2;
+}
 
 template <int BN>
-int32_t launch_tc(const TcArgs &a, cudaStream_t stream)
+int32_t launch_tc(const TcArgs &a, int n_kb, cudaStream_t stream)
 {
     static bool configured = false;
-    const size_t smem = smem_bytes<BN>(MAX_TAPS);
     if (!configured) {
-        CPD_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CPD_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem_bytes<BN>(MAX_TAPS, MAX_KB)));
         configured = true;
     }
     dim3 grid((unsigned)div_up(a.m_out, BM), (unsigned)(a.cout / BN));
-    gather_gemm_tc_kernel<BN><<<grid, NTHREADS, smem_bytes<BN>(a.K), stream>>>(a);
+    gather_gemm_tc_kernel<BN><<<grid, NTHREADS, smem_bytes<BN>(a.K, n_kb), stream>>>(a);
     count_launch();
     return launch_status("cpd_gather_gemm[tcgen05]");
 }
+
+inline int bn_for(int cout) { return cout >= 256 ? 256 : cout; }
 
 }  // namespace
 
 bool gather_gemm_tc_supported(int32_t cin, int32_t K, int32_t cout)
 {
-    return cin % 8 == 0 && cin >= 8 && K <= MAX_TAPS &&
+    return cin % 8 == 0 && cin >= 8 && K <= MAX_TAPS && (long long)K * cin <= (long long)MAX_KB * BKE &&
            (cout == 16 || cout == 32 || cout == 64 || cout == 128 || (cout >= 256 && cout % 256 == 0 && cout <= 2048));
 }
 
-size_t gather_gemm_tc_workspace(int64_t, int32_t, int32_t, int32_t) { return 16; }
+// workspace = the pre-swizzled bf16 hi / lo weight image
+size_t gather_gemm_tc_workspace(int64_t, int32_t cin, int32_t K, int32_t cout)
+{
+    const size_t n_kb = (size_t)div_up((long long)K * cin, BKE);
+    return 256 + n_kb * (size_t)cout * 256;
+}
 
 int32_t gather_gemm_tc(const float *x, int64_t, int32_t cin, const float *w, int32_t K, int32_t cout, const int32_t *nbr,
                        int64_t m_out, const float *bias, const float *scale, const float *shift, const float *residual,
-                       int32_t relu, float *stats, float *y, void *, size_t, cudaStream_t stream)
+                       int32_t relu, float *stats, float *y, void *ws, size_t ws_bytes, cudaStream_t stream)
 {
     CPD_REQUIRE(gather_gemm_tc_supported(cin, K, cout), CPD_ERR_UNSUPPORTED, "tcgen05 gather-GEMM: unsupported shape");
     CPD_REQUIRE((((uintptr_t)x | (uintptr_t)w | (uintptr_t)y | (uintptr_t)bias | (uintptr_t)scale | (uintptr_t)shift |
                   (uintptr_t)residual) & 15) == 0, CPD_ERR_MISALIGNED, "tcgen05 gather-GEMM: pointers must be 16-byte aligned");
-    TcArgs a{x, w, bias, scale, shift, residual, nbr, stats, y, m_out, cin, K, cout, relu};
+    CPD_REQUIRE(ws && ws_bytes >= gather_gemm_tc_workspace(m_out, cin, K, cout), CPD_ERR_WORKSPACE, "tcgen05 gather-GEMM: workspace too small");
+    uint8_t *wsplit = reinterpret_cast<uint8_t *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    const int Kf = K * cin, n_kb = (int)div_up(Kf, BKE), bn = bn_for(cout);
+    const long long chunks = (long long)n_kb * cout * 8;
+    weight_split_kernel<<<(unsigned)div_up(chunks, 256), 256, 0, stream>>>(w, cout, Kf, n_kb, bn, wsplit);
+    count_launch();
+    TcArgs a{x, bias, scale, shift, residual, wsplit, nbr, stats, y, m_out, cin, K, cout, relu};
     switch (cout) {
-        case 16: return launch_tc<16>(a, stream);
-        case 32: return launch_tc<32>(a, stream);
-        case 64: return launch_tc<64>(a, stream);
-        case 128: return launch_tc<128>(a, stream);
-        default: return launch_tc<256>(a, stream);
+        case 16: return launch_tc<16>(a, n_kb, stream);
+        case 32: return launch_tc<32>(a, n_kb, stream);
+        case 64: return launch_tc<64>(a, n_kb, stream);
+        case 128: return launch_tc<128>(a, n_kb, stream);
+        default: return launch_tc<256>(a, n_kb, stream);
     }
 }
 

@@ -38,6 +38,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc),
         "r"(idesc), "r"(accumulate) : "memory");
 }
+// kind::f16 with bf16 operands (fp32 accumulate): K = 16 per instruction
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc),
+        "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -51,6 +60,46 @@ __device__ __forceinline__ void split4(const float4 v, float4 &h, float4 &l)
     h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
     h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
     h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+}
+
+// ---- bf16x3 operand split: x = hi + lo + O(2^-18 |x|), hi = RN_bf16(x), lo = RN_bf16(x - hi) (x - hi is exact in fp32).
+// hi.hi + hi.lo + lo.hi on the bf16 tensor cores then carries ~2^-17 relative error per product, at half the
+// shared-memory bytes and half the tensor time of the 3xTF32 split.
+__device__ __forceinline__ uint32_t bf16x2_rn(float e0, float e1)      // e0 -> low half (lower address), e1 -> high half
+{
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
+    return r;
+}
+__device__ __forceinline__ void split2(float e0, float e1, uint32_t &h, uint32_t &l)
+{
+    h = bf16x2_rn(e0, e1);
+    l = bf16x2_rn(e0 - __uint_as_float(h << 16), e1 - __uint_as_float(h & 0xffff0000u));
+}
+// 8 consecutive fp32 -> 8 bf16 hi (16 bytes) + 8 bf16 lo (16 bytes)
+__device__ __forceinline__ void split8(const float4 v0, const float4 v1, uint4 &h, uint4 &l)
+{
+    split2(v0.x, v0.y, h.x, l.x);
+    split2(v0.z, v0.w, h.y, l.y);
+    split2(v1.x, v1.y, h.z, l.z);
+    split2(v1.z, v1.w, h.w, l.w);
+}
+// 4 consecutive fp32 -> 4 bf16 hi (8 bytes) + 4 bf16 lo (8 bytes)
+__device__ __forceinline__ void split4b(const float4 v, uint2 &h, uint2 &l)
+{
+    split2(v.x, v.y, h.x, l.x);
+    split2(v.z, v.w, h.y, l.y);
+}
+
+// ---- 1-D bulk copy global -> shared with mbarrier transaction accounting (TMA engine, no tensor map) ----
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t smem_dst, const void *gmem_src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols)

@@ -9,19 +9,20 @@
 // N = 256 MMA shape even for 16/32-channel layers; the price is multiplying the zero rows of missing
 // neighbours, which costs tensor time that these gather-bound layers have to spare.
 //
-// Both operands are "MN-major" for the tensor core (rows of dY / X are contiguous along cout / cin);
-// tf32 MN-major operands have exactly one legal shared-memory layout, SWIZZLE_128B_BASE32B.
+// Both operands are "MN-major" for the tensor core (rows of dY / X are contiguous along cout / cin).
+// fp32-class accuracy comes from the bf16x3 split (hi = RN(x), lo = RN(x - hi); hi.hi + lo.hi + hi.lo,
+// see spconv_tc.cu): half the shared-memory bytes and half the tensor time of a 3xTF32 split.
 //
 // One CTA = (tap group, slice of the output rows, <=128-wide cout tile AM, BN-wide (tap,cin) tile):
 //   warps 0-7  per 32-row k-block: load the dY rows (A, contiguous) and gather the X rows of each tap
 //              of the group (B; neighbour indices come from a shared-memory copy of the tap-major
-//              table, prefetched one 128-row window ahead), split into tf32 hi/lo, store swizzled;
-//   warp 8     issues 4 x 3 tcgen05.mma kind::tf32 per k-block into a main and a correction TMEM
+//              table, prefetched one 128-row window ahead), split into bf16 hi/lo, store swizzled;
+//   warp 8     issues 2 x 3 tcgen05.mma kind::f16 (K = 16 rows) per k-block into a main and a correction TMEM
 //              accumulator (A_hi.B_hi | A_lo.B_hi + A_hi.B_lo, see spconv_tc.cu);
 //   warps 0-7  finally tcgen05.ld both accumulators and add them into dW with vector fp32 reductions
 //              (split-K over row slices; dW is zeroed by the host wrapper first).
-// For cout tiles narrower than 128 only AM = 32/64 columns of the A tile exist in shared memory: the
-// descriptor's 32-column blocks beyond AM alias whatever follows, which only pollutes accumulator
+// For cout tiles narrower than 128 only one 64-column block of the A tile exists in shared memory: the
+// descriptor's second block aliases whatever follows, which only pollutes accumulator
 // lanes >= AM that are never read.
 #include "tc_common.cuh"
 
@@ -29,16 +30,17 @@ namespace cpd {
 namespace {
 using namespace tc;
 
-constexpr int KB = 32;           // rows per k-block (4 MMA K-steps of 8)
+constexpr int KB = 32;           // rows per k-block (2 MMA K-steps of 16)
 constexpr int WINR = 128;        // rows per neighbour-table window (4 k-blocks)
 constexpr int NPW = 8;            // producer / epilogue warps
 constexpr int NPROD = NPW * 32;
 constexpr int NTHREADS = NPROD + 32;
 constexpr uint32_t END_MARK = 0xffffffffu;
 constexpr int MAX_T = 32;        // taps per group (cin = 8 -> 32 taps in N = 256)
-constexpr int MAX_STEPS_PER_CTA = 512;   // k8 steps accumulated in one TMEM accumulator (bounds the truncation bias)
+constexpr int MAX_ROWS_PER_CTA = 4096;   // = 256 K-steps accumulated in one TMEM accumulator (bounds the truncation bias)
 
-__host__ __device__ constexpr int w_stage_bytes(int bn, int am) { return 2 * KB * am * 4 + 2 * KB * bn * 4; }
+__host__ __device__ constexpr int w_a_bytes(int am) { return KB * (am < 64 ? 64 : am) * 2; }   // whole 64-column blocks
+__host__ __device__ constexpr int w_stage_bytes(int bn, int am) { return 2 * w_a_bytes(am) + 2 * KB * bn * 2; }
 __host__ __device__ constexpr int w_stages(int bn, int am)
 {
     int s = (160 * 1024) / w_stage_bytes(bn, am);
@@ -46,19 +48,19 @@ __host__ __device__ constexpr int w_stages(int bn, int am)
 }
 __host__ __device__ constexpr int w_tmem_cols(int bn) { return 2 * bn < 32 ? 32 : 2 * bn; }   // main + correction
 
-// SWIZZLE_128B_BASE32B, MN-major: atom = 4 K-rows x 128 B (32 consecutive M/N elements per row); the
-// 32-byte chunk index (address bits 5-6) is XOR-ed with the row index inside the atom (bits 7-8).
-// Tile = [32 rows x cols]: 32-column blocks LBO = 4096 B apart, 4-row atoms SBO = 512 B apart.
+// SWIZZLE_128B, MN-major bf16: atom = 8 K-rows x 128 B (64 consecutive M/N elements per row); the 16-byte
+// chunk index (address bits 4-6) is XOR-ed with the row index inside the atom (bits 7-9).
+// Tile = [32 rows x cols]: 64-column blocks LBO = 4096 B apart, 8-row atoms SBO = 1024 B apart.
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr)
 {
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
-           (1ull << 46) | (1ull << 61);
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
 }
-// byte offset of the 16-byte chunk holding columns [4*c4, 4*c4+4) of row r in a [32 rows x cols] MN-major tile
+// byte offset of the 8 bytes holding columns [4*c4, 4*c4+4) of row r in a [32 rows x cols] MN-major bf16 tile
 __device__ __forceinline__ uint32_t swz_mn(int r, int c4)
 {
-    const int c32 = (c4 & 7) >> 1;                       // 32-byte chunk inside the 128-byte row
-    return (uint32_t)((c4 >> 3) * 4096 + r * 128 + ((c32 ^ (r & 3)) << 5) + ((c4 & 1) << 4));
+    const int c16 = (c4 >> 1) & 7;                       // 16-byte chunk inside the 128-byte row
+    return (uint32_t)((c4 >> 4) * 4096 + r * 128 + ((c16 ^ (r & 7)) << 4) + ((c4 & 1) << 3));
 }
 
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
@@ -78,12 +80,12 @@ template <int BN, int AM>
 __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a)
 {
     constexpr int STAGES = w_stages(BN, AM), STAGE = w_stage_bytes(BN, AM);
-    constexpr int A_BYTES = KB * AM * 4, B_BYTES = KB * BN * 4;
+    constexpr int A_BYTES = w_a_bytes(AM), B_BYTES = KB * BN * 2;
     constexpr int A_V = (KB * AM / 4) / NPROD, B_V = (KB * BN / 4) / NPROD;   // float4 per thread per k-block
     constexpr int B_C4 = BN / 4, B_RSTEP = NPROD / B_C4;                       // chunks per row; row stride between a thread's chunks
     static_assert(NPROD % B_C4 == 0 || B_C4 % NPROD == 0, "B mapping");
-    // a_major = b_major = MN (bits 15, 16), fp32 accumulate, tf32 operands, M = 128
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+    // a_major = b_major = MN (bits 15, 16), fp32 accumulate, bf16 operands, M = 128
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
                                ((uint32_t)(128 >> 4) << 24);
 
     extern __shared__ uint8_t smem_raw[];
@@ -181,22 +183,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
 #pragma unroll
             for (int j = 0; j < A_V; ++j) {
                 if (!a_live[j]) continue;
-                float4 h, l;
-                split4(av[j], h, l);
-                *reinterpret_cast<float4 *>(st + a_off[j]) = h;
-                *reinterpret_cast<float4 *>(st + A_BYTES + a_off[j]) = l;
+                uint2 h, l;
+                split4b(av[j], h, l);
+                *reinterpret_cast<uint2 *>(st + a_off[j]) = h;
+                *reinterpret_cast<uint2 *>(st + A_BYTES + a_off[j]) = l;
             }
             if (b_live) {
 #pragma unroll
                 for (int j = 0; j < B_V; ++j) {
-                    float4 h, l;
-                    split4(bv[j], h, l);
-                    *reinterpret_cast<float4 *>(st + 2 * A_BYTES + b_off[j]) = h;
-                    *reinterpret_cast<float4 *>(st + 2 * A_BYTES + B_BYTES + b_off[j]) = l;
+                    uint2 h, l;
+                    split4b(bv[j], h, l);
+                    *reinterpret_cast<uint2 *>(st + 2 * A_BYTES + b_off[j]) = h;
+                    *reinterpret_cast<uint2 *>(st + 2 * A_BYTES + B_BYTES + b_off[j]) = l;
                 }
             }
             const int nvalid = (int)min((long long)KB, r_end - (r_begin + (long long)blk * KB));
-            if (tid == 0) info[s] = (uint32_t)((nvalid + 7) / 8);
+            if (tid == 0) info[s] = (uint32_t)((nvalid + 15) / 16);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(full0 + 8 * s);      // one arrival per producer warp
@@ -271,19 +273,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
         for (;; ++it) {
             const int s = it % STAGES;
             mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
-            const uint32_t k8n = *reinterpret_cast<volatile uint32_t *>(&info[s]);
-            if (k8n == END_MARK) break;
+            const uint32_t k16n = *reinterpret_cast<volatile uint32_t *>(&info[s]);
+            if (k16n == END_MARK) break;
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t st = smem_u32(tiles + s * STAGE);
                 const uint64_t a_hi = make_desc_mn(st), a_lo = make_desc_mn(st + A_BYTES);
                 const uint64_t b_hi = make_desc_mn(st + 2 * A_BYTES), b_lo = make_desc_mn(st + 2 * A_BYTES + B_BYTES);
                 const uint32_t d_main = tmem_base, d_corr = tmem_base + (uint32_t)BN;
-                for (uint32_t k8 = 0; k8 < k8n; ++k8) {
-                    const uint64_t adv = (uint64_t)((k8 * 1024) >> 4);     // next 8-row K step (two 4-row atoms)
-                    umma_tf32(d_main, a_hi + adv, b_hi + adv, IDESC, (it | (int)k8) ? 1u : 0u);
-                    umma_tf32(d_corr, a_lo + adv, b_hi + adv, IDESC, (it | (int)k8) ? 1u : 0u);
-                    umma_tf32(d_corr, a_hi + adv, b_lo + adv, IDESC, 1u);
+                for (uint32_t k16 = 0; k16 < k16n; ++k16) {
+                    const uint64_t adv = (uint64_t)((k16 * 2048) >> 4);     // next 16-row K step (two 8-row atoms)
+                    umma_bf16(d_main, a_hi + adv, b_hi + adv, IDESC, (it | (int)k16) ? 1u : 0u);
+                    umma_bf16(d_corr, a_lo + adv, b_hi + adv, IDESC, (it | (int)k16) ? 1u : 0u);
+                    umma_bf16(d_corr, a_hi + adv, b_lo + adv, IDESC, 1u);
                 }
                 umma_commit(empty0 + 8 * s);
             }
@@ -354,7 +356,7 @@ int32_t gather_wgrad_rows_tc(const float *x, int32_t cin, const float *dy, int64
     const int groups = (int)div_up(K, tpg), co_tiles = (int)div_up(cout, 128);
     // row slices: enough CTAs for ~2 per SM, but at most MAX_STEPS_PER_CTA k8 steps per accumulator
     long long S = div_up(148 * 2, (long long)groups * ci_tiles * co_tiles);
-    const long long min_s = div_up(m_out, (long long)MAX_STEPS_PER_CTA * 8);
+    const long long min_s = div_up(m_out, (long long)MAX_ROWS_PER_CTA);
     if (S < min_s) S = min_s;
     const long long max_s = div_up(m_out, WINR);
     if (S > max_s) S = max_s;
