@@ -10,16 +10,17 @@
 
 namespace cpd {
 
-int32_t gather_gemm_tc(const float *x, int64_t m_in, int32_t cin, const float *w, int32_t K, int32_t cout,
+int32_t split_rows(const float *x, int64_t m, int32_t c, void *xs, cudaStream_t stream);
+int32_t gather_gemm_tc(const void *xs, int32_t cin, const float *w, int32_t K, int32_t cout,
                        const int32_t *nbr, int64_t m_out, const float *bias, const float *scale, const float *shift,
                        const float *residual, int32_t relu, float *stats, float *y, void *ws, size_t ws_bytes,
                        cudaStream_t stream);
-size_t gather_gemm_tc_workspace(int64_t m_out, int32_t cin, int32_t K, int32_t cout);
+size_t gather_gemm_tc_workspace(int32_t cin, int32_t K, int32_t cout);
 bool gather_gemm_tc_supported(int32_t cin, int32_t K, int32_t cout);
 // two tcgen05 weight-gradient kernels: row-stationary with taps along N (wgrad_tc.cu, best for C_in <= 32, needs the
 // tap-major table) and per-tap pair lists (wgrad_pairs_tc.cu, best for C_in >= 64)
 bool gather_wgrad_rows_supported(int32_t cin, int32_t K, int32_t cout);
-int32_t gather_wgrad_rows_tc(const float *x, int32_t cin, const float *dy, int64_t m_out, int32_t cout, const int32_t *nbr_t,
+int32_t gather_wgrad_rows_tc(const void *xs, int32_t cin, const void *dys, int64_t m_out, int32_t cout, const int32_t *nbr_t,
                              int32_t K, float *dw, cudaStream_t stream);
 bool gather_wgrad_pairs_supported(int32_t cin, int32_t K, int32_t cout);
 int32_t gather_wgrad_pairs_tc(const float *x, int32_t cin, const float *dy, int64_t m_out, int32_t cout, const int32_t *nbr,
@@ -328,33 +329,50 @@ __global__ void dense_scatter_kernel(const float *__restrict__ src, const int32_
 
 using namespace cpd;
 
-extern "C" size_t cpd_gather_gemm_workspace_bytes(int64_t m_out, int32_t cin, int32_t K, int32_t cout, int32_t algo)
+static size_t image_bytes(int64_t m, int32_t c) { return align_up((size_t)m * (size_t)c * 4, 256); }   // split-row image of an (m, c) matrix
+
+extern "C" size_t cpd_gather_gemm_workspace_bytes(int64_t m_in, int64_t, int32_t cin, int32_t K, int32_t cout, int32_t algo,
+                                                  int32_t have_x_split)
 {
     if (algo == CPD_ALGO_SIMT) return 0;
     if (!gather_gemm_tc_supported(cin, K, cout)) return 0;
-    return gather_gemm_tc_workspace(m_out, cin, K, cout);
+    return 256 + gather_gemm_tc_workspace(cin, K, cout) + (have_x_split ? 0 : image_bytes(m_in, cin));
 }
 
-extern "C" int32_t cpd_gather_gemm(const float *x, int64_t m_in, int32_t cin, const float *w, int32_t K, int32_t cout,
-                                   const int32_t *nbr, int64_t m_out, const float *bias, const float *scale,
+extern "C" int32_t cpd_gather_gemm(const float *x, const void *x_split, int64_t m_in, int32_t cin, const float *w, int32_t K,
+                                   int32_t cout, const int32_t *nbr, int64_t m_out, const float *bias, const float *scale,
                                    const float *shift, const float *residual, int32_t relu, float *stats, float *y,
                                    int32_t algo, void *ws, size_t ws_bytes, cpd_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
-    CPD_REQUIRE(x && w && nbr && y, CPD_ERR_BAD_ARG, "cpd_gather_gemm: null argument");
+    CPD_REQUIRE((x || x_split) && w && nbr && y, CPD_ERR_BAD_ARG, "cpd_gather_gemm: null argument");
     CPD_REQUIRE(m_in >= 0 && m_out >= 0 && cin >= 1 && cout >= 1 && K >= 1 && K <= 64, CPD_ERR_BAD_ARG, "cpd_gather_gemm: bad sizes");
     CPD_REQUIRE((scale == nullptr) == (shift == nullptr), CPD_ERR_BAD_ARG, "cpd_gather_gemm: scale and shift go together");
     CPD_REQUIRE(m_out < (1ll << 31) && m_in < (1ll << 31), CPD_ERR_UNSUPPORTED, "cpd_gather_gemm: more than 2^31 rows");
     if (m_out == 0) return CPD_OK;
+    const size_t need = cpd_gather_gemm_workspace_bytes(m_in, m_out, cin, K, cout, CPD_ALGO_TCGEN05, x_split != nullptr);
     bool tc = false;
     if (algo == CPD_ALGO_TCGEN05) {
-        CPD_REQUIRE(gather_gemm_tc_supported(cin, K, cout), CPD_ERR_UNSUPPORTED, "cpd_gather_gemm: tcgen05 path needs cin%%8==0, cout%%16==0, cout<=256");
+        CPD_REQUIRE(gather_gemm_tc_supported(cin, K, cout), CPD_ERR_UNSUPPORTED, "cpd_gather_gemm: tcgen05 path needs cin%%8==0, cout in {16,32,64,128,256k}");
+        CPD_REQUIRE(ws && ws_bytes >= need, CPD_ERR_WORKSPACE, "cpd_gather_gemm: workspace too small (cpd_gather_gemm_workspace_bytes)");
         tc = true;
     } else if (algo == CPD_ALGO_AUTO) {
         static const int min_cin = getenv("CPD_TC_MIN_CIN") ? atoi(getenv("CPD_TC_MIN_CIN")) : 16;   // tuning knob
-        tc = gather_gemm_tc_supported(cin, K, cout) && cin >= min_cin && ws && ws_bytes >= gather_gemm_tc_workspace(m_out, cin, K, cout);
+        tc = gather_gemm_tc_supported(cin, K, cout) && cin >= min_cin && ws && ws_bytes >= need;
     }
-    if (tc) return gather_gemm_tc(x, m_in, cin, w, K, cout, nbr, m_out, bias, scale, shift, residual, relu, stats, y, ws, ws_bytes, stream);
+    if (tc) {
+        uint8_t *p = reinterpret_cast<uint8_t *>(align_up((size_t)(uintptr_t)ws, 256));
+        const void *xs = x_split;
+        if (!xs) {                                   // build the split-row image of x in the workspace
+            int32_t st = split_rows(x, m_in, cin, p, stream);
+            if (st) return st;
+            xs = p;
+            p += image_bytes(m_in, cin);
+        }
+        const size_t left = ws_bytes - (size_t)(p - reinterpret_cast<uint8_t *>(ws));
+        return gather_gemm_tc(xs, cin, w, K, cout, nbr, m_out, bias, scale, shift, residual, relu, stats, y, p, left, stream);
+    }
+    CPD_REQUIRE(x, CPD_ERR_BAD_ARG, "cpd_gather_gemm: the SIMT kernel needs the fp32 rows");
     Epilogue ep{bias, scale, shift, residual, stats, relu};
     if (cout > 32) launch_gg<64, 64, 4, 4>(x, cin, w, K, cout, nbr, m_out, ep, y, stream);
     else if (cout > 16) launch_gg<128, 32, 4, 4>(x, cin, w, K, cout, nbr, m_out, ep, y, stream);
@@ -362,11 +380,17 @@ extern "C" int32_t cpd_gather_gemm(const float *x, int64_t m_in, int32_t cin, co
     return launch_status("cpd_gather_gemm");
 }
 
-extern "C" size_t cpd_gather_wgrad_workspace_bytes(int64_t, int32_t, int32_t, int32_t) { return 0; }
+extern "C" size_t cpd_gather_wgrad_workspace_bytes(int64_t m_in, int64_t m_out, int32_t cin, int32_t K, int32_t cout,
+                                                   int32_t have_x_split, int32_t have_dy_split)
+{
+    if (!gather_wgrad_rows_supported(cin, K, cout)) return 0;
+    return 256 + (have_x_split ? 0 : image_bytes(m_in, cin)) + (have_dy_split ? 0 : image_bytes(m_out, cout));
+}
 
-extern "C" int32_t cpd_gather_wgrad(const float *x, int64_t m_in, int32_t cin, const float *dy, int64_t m_out,
-                                    int32_t cout, const int32_t *nbr, int32_t nbr_tap_major, int32_t K, float *dw,
-                                    float *dbias, int32_t algo, void *, size_t, cpd_stream_t stream_)
+extern "C" int32_t cpd_gather_wgrad(const float *x, const void *x_split, int64_t m_in, int32_t cin, const float *dy,
+                                    const void *dy_split, int64_t m_out, int32_t cout, const int32_t *nbr,
+                                    int32_t nbr_tap_major, int32_t K, float *dw, float *dbias, int32_t algo, void *ws,
+                                    size_t ws_bytes, cpd_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     CPD_REQUIRE(x && dy && nbr && dw, CPD_ERR_BAD_ARG, "cpd_gather_wgrad: null argument");
@@ -375,24 +399,37 @@ extern "C" int32_t cpd_gather_wgrad(const float *x, int64_t m_in, int32_t cin, c
     if (dbias) CPD_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)cout, stream));
     if (m_out == 0) return CPD_OK;
     const bool tap_major_ok = nbr_tap_major || K == 1;
-    const bool rows_ok = gather_wgrad_rows_supported(cin, K, cout) && tap_major_ok;
+    const size_t need = cpd_gather_wgrad_workspace_bytes(m_in, m_out, cin, K, cout, x_split != nullptr, dy_split != nullptr);
+    const bool rows_ok = gather_wgrad_rows_supported(cin, K, cout) && tap_major_ok && ws && ws_bytes >= need;
     const bool pairs_ok = gather_wgrad_pairs_supported(cin, K, cout);
-    static const int rows_max_cin = getenv("CPD_WGRAD_ROWS_MAX_CIN") ? atoi(getenv("CPD_WGRAD_ROWS_MAX_CIN")) : 1024;   // tuning knob
+    static const bool force_pairs = getenv("CPD_WGRAD_FORCE_PAIRS") != nullptr;                        // tuning knob
     bool tc = false;
     if (algo == CPD_ALGO_TCGEN05) {
-        CPD_REQUIRE(rows_ok || pairs_ok, CPD_ERR_UNSUPPORTED, "cpd_gather_wgrad: tcgen05 path needs cin, cout >= 8 and multiples of 4");
+        CPD_REQUIRE(rows_ok || pairs_ok, CPD_ERR_UNSUPPORTED, "cpd_gather_wgrad: tcgen05 path needs cin, cout >= 8 and multiples of 8 (and its workspace)");
         tc = true;
     } else if (algo == CPD_ALGO_AUTO) {
         tc = rows_ok || pairs_ok;
     }
     if (tc) {
         int32_t st;
-        // measured on B200 (tools/wg_check.py, tools/prof_layer.py): the row-stationary kernel wins everywhere except
-        // wide-in AND wide-out layers (256 -> 256), where the per-tap pair-list kernel's N = 256, M = 2 x 128 tiling is better
-        static const bool force_rows = getenv("CPD_WGRAD_FORCE_ROWS") != nullptr;                        // tuning knob
-        const bool prefer_rows = force_rows || (cin <= rows_max_cin && !(cin >= 256 && cout >= 256));
-        if (rows_ok && (prefer_rows || !pairs_ok)) st = gather_wgrad_rows_tc(x, cin, dy, m_out, cout, nbr, K, dw, stream);
-        else st = gather_wgrad_pairs_tc(x, cin, dy, m_out, cout, nbr, K, nbr_tap_major, dw, stream);
+        if (rows_ok && !(force_pairs && pairs_ok)) {
+            uint8_t *p = reinterpret_cast<uint8_t *>(align_up((size_t)(uintptr_t)ws, 256));
+            const void *xs = x_split, *dys = dy_split;
+            if (!xs) {
+                st = split_rows(x, m_in, cin, p, stream);
+                if (st) return st;
+                xs = p;
+                p += image_bytes(m_in, cin);
+            }
+            if (!dys) {
+                st = split_rows(dy, m_out, cout, p, stream);
+                if (st) return st;
+                dys = p;
+            }
+            st = gather_wgrad_rows_tc(xs, cin, dys, m_out, cout, nbr, K, dw, stream);
+        } else {
+            st = gather_wgrad_pairs_tc(x, cin, dy, m_out, cout, nbr, K, nbr_tap_major, dw, stream);
+        }
         if (st) return st;
     }
     const int co_tiles = (int)div_up(cout, 64), ci_tiles = (int)div_up(cin, 64);

@@ -17,11 +17,12 @@
 //              [hi | lo] block of 2 * BN * 128 bytes per (k-block, cout tile).
 //   warp 9     per k-block ONE cp.async.bulk (TMA engine, no tensor map needed because the image
 //              is pre-swizzled) brings the B tile in, completing on the stage's full barrier.
-//   warps 0-7  producers: gather A rows (x[nbr[o,k]], 32 bytes of fp32 per thread per row) straight
-//              from global/L2, split every fp32 into bf16 hi + lo in registers and store both into
-//              shared memory in the canonical K-major SWIZZLE_128B layout that UMMA descriptors
-//              address (gathered rows are not TMA-tileable and the split has to pass through
-//              registers anyway).  fence.proxy.async + mbarrier arrive hand the stage over.
+//   warps 0-7  producers: gather A rows from the split-row image of x (split.cu: every row is split
+//              into bf16 hi | lo ONCE per layer, not once per rulebook pair) with 16-byte cp.async
+//              straight into the canonical K-major SWIZZLE_128B layout that UMMA descriptors address:
+//              no register staging, no conversion work in the loop, missing neighbours zero-filled by
+//              the copy itself (src-size 0), STAGES-1 k-blocks in flight per thread.  Completed groups
+//              are handed over with cp.async.wait_group + fence.proxy.async + mbarrier arrive.
 //              k-blocks none of whose taps has a neighbour in the tile are skipped altogether.
 //   warp 8     allocates TMEM, then one elected lane issues per k-block 4 x 3
 //              tcgen05.mma.cta_group::1.kind::f16 (A_hi.B_hi + A_lo.B_hi + A_hi.B_lo, M=128,
@@ -77,7 +78,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
 __host__ __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
 
 struct TcArgs {
-    const float *x, *bias, *scale, *shift, *residual;
+    const float *bias, *scale, *shift, *residual;
+    const uint8_t *xs;          // split-row image of x: row i = [hi(cin) | lo(cin)] bf16
     const uint8_t *wsplit;      // [k-block][cout tile][hi | lo][BN rows x 128 B, swizzled]
     const int32_t *nbr;
     float *stats, *y;
@@ -183,52 +185,40 @@ __global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kern
 
     if (warp < NPW) {
         // ================= producers =================
-        // Software-pipelined: the gather loads of k-block it+1 are in flight while k-block it is
-        // split and stored (register double buffering).
         const int c = tid & 7, r_base = tid >> 3;   // 16-byte smem chunk (8 channels), first row (rows r_base + RSTEP j)
         uint32_t soff[A_V];                         // swizzled byte offsets of this thread's chunks (loop invariant)
 #pragma unroll
         for (int j = 0; j < A_V; ++j) soff[j] = swz(r_base + RSTEP * j, c);
-        auto load = [&](int it, float4(&av)[2 * A_V]) {
-            const int f = (int)kb_list[it] * BKE + c * 8;            // flattened (tap, channel) index of this thread's chunk
-            const int k = f / a.cin, ch = f - k * a.cin;
-            const int32_t *nb = nbr_s + (k < a.K ? k : 0) * BM + r_base;
-#pragma unroll
-            for (int j = 0; j < A_V; ++j) {
-                const int32_t idx = k < a.K ? nb[RSTEP * j] : -1;
-                if (idx >= 0) {
-                    const float4 *p = reinterpret_cast<const float4 *>(a.x + (size_t)idx * a.cin + ch);
-                    av[2 * j] = __ldg(p); av[2 * j + 1] = __ldg(p + 1);
-                } else {
-                    av[2 * j] = make_float4(0.f, 0.f, 0.f, 0.f); av[2 * j + 1] = av[2 * j];
-                }
-            }
-        };
-        auto store = [&](int it, const float4(&av)[2 * A_V]) {
+        const uint32_t tiles_u32 = smem_u32(tiles);
+        const size_t row_bytes = (size_t)a.cin * 4;                // image row = hi(cin) | lo(cin) bf16
+        const uint32_t lo_off = (uint32_t)a.cin * 2;
+        auto issue = [&](int it) {
             const int s = it % STAGES;
             mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
-            uint8_t *st = tiles + s * STAGE;
+            const int f = (int)kb_list[it] * BKE + c * 8;            // flattened (tap, channel) index of this thread's chunk
+            const int k = f / a.cin, ch = f - k * a.cin;
+            const bool k_ok = k < a.K;
+            const int32_t *nb = nbr_s + (k_ok ? k : 0) * BM + r_base;
+            const uint32_t dst = tiles_u32 + (uint32_t)(s * STAGE);
+            const uint8_t *col = a.xs + (size_t)ch * 2;
 #pragma unroll
             for (int j = 0; j < A_V; ++j) {
-                uint4 h, l;
-                split8(av[2 * j], av[2 * j + 1], h, l);
-                *reinterpret_cast<uint4 *>(st + soff[j]) = h;
-                *reinterpret_cast<uint4 *>(st + A_BYTES + soff[j]) = l;
+                const int32_t idx = k_ok ? nb[RSTEP * j] : -1;
+                const uint8_t *src = col + (size_t)(idx >= 0 ? idx : 0) * row_bytes;
+                const uint32_t sz = idx >= 0 ? 16u : 0u;                 // 0 -> the copy writes 16 zero bytes
+                cp_async16(dst + soff[j], src, sz);
+                cp_async16(dst + A_BYTES + soff[j], src + lo_off, sz);
             }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full0 + 8 * s);      // one arrival per producer warp
         };
-        if (n_iters > 0) {
-            float4 a0[2 * A_V], a1[2 * A_V];
-            load(0, a0);
-            for (int it = 0; it < n_iters; it += 2) {
-                if (it + 1 < n_iters) load(it + 1, a1);
-                store(it, a0);
-                if (it + 1 < n_iters) {
-                    if (it + 2 < n_iters) load(it + 2, a0);
-                    store(it + 1, a1);
-                }
+        constexpr int D = STAGES - 1;               // k-blocks in flight per thread
+        for (int it = 0; it < n_iters + D; ++it) {
+            if (it < n_iters) issue(it);
+            cp_async_commit();
+            if (it >= D) {
+                cp_async_wait<D>();                  // group it - D has landed
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full0 + 8 * ((it - D) % STAGES));      // one arrival per producer warp
             }
         }
         // ================= epilogue =================
@@ -376,26 +366,26 @@ bool gather_gemm_tc_supported(int32_t cin, int32_t K, int32_t cout)
 }
 
 // workspace = the pre-swizzled bf16 hi / lo weight image
-size_t gather_gemm_tc_workspace(int64_t, int32_t cin, int32_t K, int32_t cout)
+size_t gather_gemm_tc_workspace(int32_t cin, int32_t K, int32_t cout)
 {
     const size_t n_kb = (size_t)div_up((long long)K * cin, BKE);
     return 256 + n_kb * (size_t)cout * 256;
 }
 
-int32_t gather_gemm_tc(const float *x, int64_t, int32_t cin, const float *w, int32_t K, int32_t cout, const int32_t *nbr,
+int32_t gather_gemm_tc(const void *xs, int32_t cin, const float *w, int32_t K, int32_t cout, const int32_t *nbr,
                        int64_t m_out, const float *bias, const float *scale, const float *shift, const float *residual,
                        int32_t relu, float *stats, float *y, void *ws, size_t ws_bytes, cudaStream_t stream)
 {
     CPD_REQUIRE(gather_gemm_tc_supported(cin, K, cout), CPD_ERR_UNSUPPORTED, "tcgen05 gather-GEMM: unsupported shape");
-    CPD_REQUIRE((((uintptr_t)x | (uintptr_t)w | (uintptr_t)y | (uintptr_t)bias | (uintptr_t)scale | (uintptr_t)shift |
+    CPD_REQUIRE((((uintptr_t)xs | (uintptr_t)w | (uintptr_t)y | (uintptr_t)bias | (uintptr_t)scale | (uintptr_t)shift |
                   (uintptr_t)residual) & 15) == 0, CPD_ERR_MISALIGNED, "tcgen05 gather-GEMM: pointers must be 16-byte aligned");
-    CPD_REQUIRE(ws && ws_bytes >= gather_gemm_tc_workspace(m_out, cin, K, cout), CPD_ERR_WORKSPACE, "tcgen05 gather-GEMM: workspace too small");
+    CPD_REQUIRE(ws && ws_bytes >= gather_gemm_tc_workspace(cin, K, cout), CPD_ERR_WORKSPACE, "tcgen05 gather-GEMM: workspace too small");
     uint8_t *wsplit = reinterpret_cast<uint8_t *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     const int Kf = K * cin, n_kb = (int)div_up(Kf, BKE), bn = bn_for(cout);
     const long long chunks = (long long)n_kb * cout * 8;
     weight_split_kernel<<<(unsigned)div_up(chunks, 256), 256, 0, stream>>>(w, cout, Kf, n_kb, bn, wsplit);
     count_launch();
-    TcArgs a{x, bias, scale, shift, residual, wsplit, nbr, stats, y, m_out, cin, K, cout, relu};
+    TcArgs a{bias, scale, shift, residual, reinterpret_cast<const uint8_t *>(xs), wsplit, nbr, stats, y, m_out, cin, K, cout, relu};
     switch (cout) {
         case 16: return launch_tc<16>(a, n_kb, stream);
         case 32: return launch_tc<32>(a, n_kb, stream);

@@ -1,0 +1,51 @@
+// Split-row images: the operand format of the tcgen05 kernels.
+//
+// A row matrix X (m, c) fp32, c % 8 == 0, becomes XS (m, 2, c) bf16: row i = [hi(c) | lo(c)] with
+// hi = RN_bf16(x), lo = RN_bf16(x - hi) (x = hi + lo up to 2^-18 |x|).  The image has exactly the byte
+// size and row pitch (4 c bytes) of X, so a gather moves the same bytes as an fp32 gather -- but the
+// rows can then be copied global -> shared with 16-byte cp.async (no register staging, no conversion
+// ALU work in the gather loop, deep pipelining), and every row is split ONCE per layer instead of
+// once per rulebook pair (a voxel row is gathered by ~12-17 neighbours).
+// HBM-bound streaming kernel: 4 B read + 4 B written per element.
+#include "tc_common.cuh"
+
+namespace cpd {
+namespace {
+
+__global__ void split_rows_kernel(const float *__restrict__ x, long long n_chunks, int c8_per_row, uint8_t *__restrict__ xs)
+{
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_chunks; t += (long long)gridDim.x * blockDim.x) {
+        const long long row = t / c8_per_row;
+        const int c8 = (int)(t - row * c8_per_row);
+        const float4 *p = reinterpret_cast<const float4 *>(x) + t * 2;
+        const float4 v0 = __ldg(p), v1 = __ldg(p + 1);
+        uint4 h, l;
+        tc::split8(v0, v1, h, l);
+        uint8_t *dst = xs + (size_t)row * (size_t)(c8_per_row * 32) + (size_t)c8 * 16;
+        *reinterpret_cast<uint4 *>(dst) = h;
+        *reinterpret_cast<uint4 *>(dst + (size_t)c8_per_row * 16) = l;
+    }
+}
+
+}  // namespace
+
+int32_t split_rows(const float *x, int64_t m, int32_t c, void *xs, cudaStream_t stream)
+{
+    CPD_REQUIRE(c >= 8 && c % 8 == 0, CPD_ERR_UNSUPPORTED, "cpd_split_rows: channels must be a multiple of 8");
+    CPD_REQUIRE((((uintptr_t)x | (uintptr_t)xs) & 15) == 0, CPD_ERR_MISALIGNED, "cpd_split_rows: pointers must be 16-byte aligned");
+    if (m == 0) return CPD_OK;
+    const long long n_chunks = (long long)m * (c / 8);
+    long long blocks = div_up(n_chunks, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;          // grid-stride: 16 CTAs of 256 threads per SM
+    split_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, n_chunks, c / 8, reinterpret_cast<uint8_t *>(xs));
+    count_launch();
+    return launch_status("cpd_split_rows");
+}
+
+}  // namespace cpd
+
+extern "C" int32_t cpd_split_rows(const float *x, int64_t m, int32_t c, void *xs, cpd_stream_t stream)
+{
+    CPD_REQUIRE(x && xs && m >= 0, CPD_ERR_BAD_ARG, "cpd_split_rows: bad argument");
+    return cpd::split_rows(x, m, c, xs, (cudaStream_t)stream);
+}

@@ -102,6 +102,15 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t smem_dst, const void *gme
                  "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// ---- 16-byte asynchronous copies global -> shared (LDGSTS); src_size = 0 zero-fills the destination ----
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gmem_src, uint32_t src_size)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_size) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols)
 {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols));

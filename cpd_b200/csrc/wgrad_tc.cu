@@ -14,9 +14,11 @@
 // see spconv_tc.cu): half the shared-memory bytes and half the tensor time of a 3xTF32 split.
 //
 // One CTA = (tap group, slice of the output rows, <=128-wide cout tile AM, BN-wide (tap,cin) tile):
-//   warps 0-7  per 32-row k-block: load the dY rows (A, contiguous) and gather the X rows of each tap
+//   warps 0-7  per 32-row k-block: copy the dY rows (A, contiguous) and gather the X rows of each tap
 //              of the group (B; neighbour indices come from a shared-memory copy of the tap-major
-//              table, prefetched one 128-row window ahead), split into bf16 hi/lo, store swizzled;
+//              table, prefetched one 128-row window ahead) from the split-row images (split.cu) with
+//              16-byte cp.async straight into the swizzled tiles -- no register staging, missing
+//              neighbours zero-filled by the copy, STAGES-1 k-blocks in flight per thread;
 //   warp 8     issues 2 x 3 tcgen05.mma kind::f16 (K = 16 rows) per k-block into a main and a correction TMEM
 //              accumulator (A_hi.B_hi | A_lo.B_hi + A_hi.B_lo, see spconv_tc.cu);
 //   warps 0-7  finally tcgen05.ld both accumulators and add them into dW with vector fp32 reductions
@@ -56,11 +58,10 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr)
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
            (1ull << 46) | (2ull << 61);
 }
-// byte offset of the 8 bytes holding columns [4*c4, 4*c4+4) of row r in a [32 rows x cols] MN-major bf16 tile
-__device__ __forceinline__ uint32_t swz_mn(int r, int c4)
+// byte offset of the 16 bytes holding columns [8*c8, 8*c8+8) of row r in a [32 rows x cols] MN-major bf16 tile
+__device__ __forceinline__ uint32_t swz_mn(int r, int c8)
 {
-    const int c16 = (c4 >> 1) & 7;                       // 16-byte chunk inside the 128-byte row
-    return (uint32_t)((c4 >> 4) * 4096 + r * 128 + ((c16 ^ (r & 7)) << 4) + ((c4 & 1) << 3));
+    return (uint32_t)((c8 >> 3) * 4096 + r * 128 + (((c8 & 7) ^ (r & 7)) << 4));
 }
 
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
@@ -69,7 +70,7 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 }
 
 struct WgArgs {
-    const float *x, *dy;
+    const uint8_t *xs, *dys;     // split-row images: row i = [hi(c) | lo(c)] bf16
     const int32_t *nbr_t;        // tap-major table (K, m_out)
     float *dw;
     long long m_out;
@@ -81,9 +82,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
 {
     constexpr int STAGES = w_stages(BN, AM), STAGE = w_stage_bytes(BN, AM);
     constexpr int A_BYTES = w_a_bytes(AM), B_BYTES = KB * BN * 2;
-    constexpr int A_V = (KB * AM / 4) / NPROD, B_V = (KB * BN / 4) / NPROD;   // float4 per thread per k-block
-    constexpr int B_C4 = BN / 4, B_RSTEP = NPROD / B_C4;                       // chunks per row; row stride between a thread's chunks
-    static_assert(NPROD % B_C4 == 0 || B_C4 % NPROD == 0, "B mapping");
+    constexpr int A_C8 = AM / 8, A_V = (KB * A_C8 + NPROD - 1) / NPROD;        // 16-byte chunks per row / per thread per k-block
+    constexpr int B_C8 = BN / 8, B_RSTEP = NPROD / B_C8, B_V = KB / B_RSTEP;   // chunks per row; row stride between a thread's chunks
+    static_assert(NPROD % B_C8 == 0 && KB % B_RSTEP == 0, "B mapping");
     // a_major = b_major = MN (bits 15, 16), fp32 accumulate, bf16 operands, M = 128
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
                                ((uint32_t)(128 >> 4) << 24);
@@ -121,26 +122,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
     if (warp < NPW) {
         // Zero all operand stages once: columns beyond cout / (T*cin) are never written again.
         for (int e = tid; e < STAGES * STAGE / 16; e += NPROD) reinterpret_cast<float4 *>(tiles)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        // loop-invariant mapping.  A: e = tid + 128 j over 32 x (AM/4) chunks.
+        // loop-invariant mapping.  A: e = tid + 256 j over 32 x (AM/8) 16-byte chunks.
         uint32_t a_off[A_V];
         int a_row[A_V], a_col[A_V];
         bool a_live[A_V];
 #pragma unroll
         for (int j = 0; j < A_V; ++j) {
             const int e = tid + NPROD * j;
-            a_row[j] = e / (AM / 4); a_col[j] = co0 + (e % (AM / 4)) * 4;
-            a_off[j] = swz_mn(a_row[j], e % (AM / 4)); a_live[j] = a_col[j] < a.cout;
+            a_row[j] = e / A_C8; a_col[j] = co0 + (e % A_C8) * 8;
+            a_off[j] = swz_mn(a_row[j], e % A_C8); a_live[j] = a_row[j] < KB && a_col[j] < a.cout;
         }
         // B: this thread owns ONE column chunk (fixed tap and channel offset) and rows b_row0 + B_RSTEP*j.
-        const int b_c4 = tid % B_C4, b_row0 = tid / B_C4;
-        const int b_colv = b_c4 * 4;
+        const int b_c8 = tid % B_C8, b_row0 = tid / B_C8;
+        const int b_colv = b_c8 * 8;
         const int b_t = a.cin >= BN ? 0 : b_colv / a.cin;                  // tap inside the group
         const int b_ci = a.cin >= BN ? ci0 + b_colv : b_colv % a.cin;      // input channel of the chunk
         const bool b_live = b_t < T && b_ci < a.cin;
         uint32_t b_off[B_V];
 #pragma unroll
-        for (int j = 0; j < B_V; ++j) b_off[j] = swz_mn(b_row0 + B_RSTEP * j, b_c4);
+        for (int j = 0; j < B_V; ++j) b_off[j] = swz_mn(b_row0 + B_RSTEP * j, b_c8);
         const int my_nbr_off = b_t * WINR + b_row0;
+        const uint32_t tiles_u32 = smem_u32(tiles);
+        const size_t x_row = (size_t)a.cin * 4, dy_row = (size_t)a.cout * 4;       // image rows: hi(c) | lo(c)
+        const uint32_t x_lo = (uint32_t)a.cin * 2, dy_lo = (uint32_t)a.cout * 2;
 
         // ---- neighbour-table windows (T x 128 entries): fetched into registers two windows ahead, published into
         //      a double-buffered shared-memory copy one window ahead of the gathers that read it ----
@@ -161,50 +165,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
                 if (e / WINR < T) nbr_w[buf * MAX_T * WINR + e] = nreg[q];
             }
         };
-        int it = 0;
-        auto load = [&](int blk, float4(&av)[A_V], float4(&bv)[B_V]) {
+        auto issue = [&](int blk) {
+            const int s = blk % STAGES;
+            mbar_wait(empty0 + 8 * s, ((blk / STAGES) & 1) ^ 1);
             const long long r0 = r_begin + (long long)blk * KB;
             const int nvalid = (int)min((long long)KB, r_end - r0);
             const int32_t *tab = nbr_w + ((blk / (WINR / KB)) & 1) * MAX_T * WINR + my_nbr_off + (blk % (WINR / KB)) * KB;
-#pragma unroll
-            for (int j = 0; j < A_V; ++j)
-                av[j] = (a_live[j] && a_row[j] < nvalid) ? __ldg(reinterpret_cast<const float4 *>(a.dy + (r0 + a_row[j]) * a.cout + a_col[j]))
-                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < B_V; ++j) {
-                const int32_t idx = b_live ? tab[B_RSTEP * j] : -1;
-                bv[j] = idx >= 0 ? __ldg(reinterpret_cast<const float4 *>(a.x + (size_t)idx * a.cin + b_ci)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        };
-        auto store = [&](int blk, const float4(&av)[A_V], const float4(&bv)[B_V]) {
-            const int s = it % STAGES;
-            mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
-            uint8_t *st = tiles + s * STAGE;
+            const uint32_t dst = tiles_u32 + (uint32_t)(s * STAGE);
 #pragma unroll
             for (int j = 0; j < A_V; ++j) {
                 if (!a_live[j]) continue;
-                uint2 h, l;
-                split4b(av[j], h, l);
-                *reinterpret_cast<uint2 *>(st + a_off[j]) = h;
-                *reinterpret_cast<uint2 *>(st + A_BYTES + a_off[j]) = l;
+                const bool ok = a_row[j] < nvalid;
+                const uint8_t *src = a.dys + (size_t)(ok ? r0 + a_row[j] : 0) * dy_row + (size_t)a_col[j] * 2;
+                cp_async16(dst + a_off[j], src, ok ? 16u : 0u);
+                cp_async16(dst + A_BYTES + a_off[j], src + dy_lo, ok ? 16u : 0u);
             }
             if (b_live) {
 #pragma unroll
                 for (int j = 0; j < B_V; ++j) {
-                    uint2 h, l;
-                    split4b(bv[j], h, l);
-                    *reinterpret_cast<uint2 *>(st + 2 * A_BYTES + b_off[j]) = h;
-                    *reinterpret_cast<uint2 *>(st + 2 * A_BYTES + B_BYTES + b_off[j]) = l;
+                    const int32_t idx = tab[B_RSTEP * j];                 // rows past r_end carry -1 in the table copy
+                    const uint8_t *src = a.xs + (size_t)(idx >= 0 ? idx : 0) * x_row + (size_t)b_ci * 2;
+                    cp_async16(dst + 2 * A_BYTES + b_off[j], src, idx >= 0 ? 16u : 0u);
+                    cp_async16(dst + 2 * A_BYTES + B_BYTES + b_off[j], src + x_lo, idx >= 0 ? 16u : 0u);
                 }
             }
+        };
+        auto complete = [&](int blk) {                                    // this thread's copies of block blk have landed
+            const int s = blk % STAGES;
             const int nvalid = (int)min((long long)KB, r_end - (r_begin + (long long)blk * KB));
             if (tid == 0) info[s] = (uint32_t)((nvalid + 15) / 16);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(full0 + 8 * s);      // one arrival per producer warp
-            ++it;
         };
-        // before block `blk` is LOADED its window's table must be published; windows are 4 blocks long
+        // before block `blk` is ISSUED its window's table must be published; windows are 4 blocks long
         auto prepare = [&](int blk) {
             if (blk % (WINR / KB) != 0 || blk >= n_blocks) return;
             const int w = blk / (WINR / KB);
@@ -216,21 +210,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
         };
         fetch_window(r_begin);
         asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");     // tiles zeroed
-        if (n_blocks > 0) {
-            float4 a0[A_V], b0v[B_V], a1[A_V], b1v[B_V];
-            prepare(0);
-            load(0, a0, b0v);
-            for (int blk = 0; blk < n_blocks; blk += 2) {
-                prepare(blk + 1);
-                if (blk + 1 < n_blocks) load(blk + 1, a1, b1v);
-                store(blk, a0, b0v);
-                if (blk + 1 < n_blocks) {
-                    prepare(blk + 2);
-                    if (blk + 2 < n_blocks) load(blk + 2, a0, b0v);
-                    store(blk + 1, a1, b1v);
-                }
+        constexpr int D = STAGES - 1;                                  // k-blocks in flight per thread
+        for (int blk = 0; blk < n_blocks + D; ++blk) {
+            if (blk < n_blocks) { prepare(blk); issue(blk); }
+            cp_async_commit();
+            if (blk >= D) {
+                cp_async_wait<D>();
+                complete(blk - D);
             }
         }
+        const int it = n_blocks;
         // ---- end marker, then epilogue ----
         {
             const int s = it % STAGES;
@@ -336,16 +325,16 @@ int32_t launch_wg_am(int am, const WgArgs &a, dim3 grid, cudaStream_t stream)
 bool gather_wgrad_rows_supported(int32_t cin, int32_t K, int32_t cout)
 {
     // cin must tile N: either a divisor-friendly small width (cin | 256 or cin | 128) or a multiple of 256
-    const bool cin_ok = cin >= 8 && cin % 4 == 0 && ((cin <= 256 && 256 % cin == 0) || cin % 256 == 0);
-    return cin_ok && cout % 4 == 0 && cout >= 8 && K <= 64;
+    const bool cin_ok = cin >= 8 && cin % 8 == 0 && ((cin <= 256 && 256 % cin == 0) || cin % 256 == 0);
+    return cin_ok && cout % 8 == 0 && cout >= 8 && K <= 64;
 }
 
 // dw must be zeroed by the caller (split-K reductions).  nbr_t: tap-major (K, m_out) table.
-int32_t gather_wgrad_rows_tc(const float *x, int32_t cin, const float *dy, int64_t m_out, int32_t cout, const int32_t *nbr_t,
+int32_t gather_wgrad_rows_tc(const void *xs, int32_t cin, const void *dys, int64_t m_out, int32_t cout, const int32_t *nbr_t,
                         int32_t K, float *dw, cudaStream_t stream)
 {
     CPD_REQUIRE(gather_wgrad_rows_supported(cin, K, cout), CPD_ERR_UNSUPPORTED, "tcgen05 wgrad: unsupported shape");
-    CPD_REQUIRE((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) == 0, CPD_ERR_MISALIGNED, "tcgen05 wgrad: pointers must be 16-byte aligned");
+    CPD_REQUIRE((((uintptr_t)xs | (uintptr_t)dys | (uintptr_t)dw) & 15) == 0, CPD_ERR_MISALIGNED, "tcgen05 wgrad: pointers must be 16-byte aligned");
     // N tile: 256 when the taps of a group (or cin itself) fill it, else 128
     const int bn = (cin >= 256 || (long long)K * cin > 128) ? 256 : 128;
     const int am = cout <= 32 ? 32 : cout <= 64 ? 64 : 128;
@@ -364,7 +353,7 @@ int32_t gather_wgrad_rows_tc(const float *x, int32_t cin, const float *dy, int64
     long long rows = div_up(div_up(m_out, S), WINR) * WINR;
     S = div_up(m_out, rows);
     CPD_REQUIRE(S <= 65535, CPD_ERR_UNSUPPORTED, "tcgen05 wgrad: too many row slices");
-    WgArgs a{x, dy, nbr_t, dw, m_out, cin, cout, K, (int)rows, ci_tiles, tpg};
+    WgArgs a{reinterpret_cast<const uint8_t *>(xs), reinterpret_cast<const uint8_t *>(dys), nbr_t, dw, m_out, cin, cout, K, (int)rows, ci_tiles, tpg};
     dim3 grid(groups, (unsigned)S, ci_tiles * co_tiles);
     if (bn == 256) return launch_wg_am<256>(am, a, grid, stream);
     return launch_wg_am<128>(am, a, grid, stream);

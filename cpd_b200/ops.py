@@ -172,9 +172,23 @@ ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05 = 0, 1, 2
 PROFILE = None
 
 
+def split_rows(x):
+    """Split-row image of a row matrix (m, c), c % 8 == 0: (m, 2, c) bf16, row = [hi(c) | lo(c)] -- the operand
+    format of the tcgen05 kernels (include/cpd_b200.h).  Returns None when the layout does not apply."""
+    _need_cuda(x)
+    if x.dim() != 2 or x.shape[1] % 8 or x.shape[1] < 8:
+        return None
+    L = _lib.lib()
+    x = _f32c(x)
+    xs = torch.empty((x.shape[0], 2, x.shape[1]), dtype=torch.bfloat16, device=x.device)
+    _lib.check(L.cpd_split_rows(_ptr(x), x.shape[0], x.shape[1], _ptr(xs), _stream()), "cpd_split_rows")
+    return xs
+
+
 def gather_gemm(x, w, nbr, bias=None, scale=None, shift=None, residual=None, relu=False, stats=None,
-                algo=ALGO_AUTO, out=None):
-    """y[o] = epi(sum_k W[:,k,:] x[nbr[o,k]]);  w is (cout, K, cin) (any (cout, ..., cin) view)."""
+                algo=ALGO_AUTO, out=None, x_split=None):
+    """y[o] = epi(sum_k W[:,k,:] x[nbr[o,k]]);  w is (cout, K, cin) (any (cout, ..., cin) view).
+    x_split: split_rows(x) if the caller already has it (shared between forward and weight-gradient)."""
     _need_cuda(x, w, nbr)
     L = _lib.lib()
     x = _f32c(x)
@@ -184,15 +198,16 @@ def gather_gemm(x, w, nbr, bias=None, scale=None, shift=None, residual=None, rel
     m_out = nbr.shape[0]
     assert nbr.shape[1] == K and nbr.dtype == torch.int32 and nbr.is_contiguous()
     assert x.shape[1] == cin
+    assert x_split is None or (x_split.shape[0] == x.shape[0] and x_split.shape[2] == cin and x_split.is_contiguous())
     y = out if out is not None else torch.empty((m_out, cout), dtype=torch.float32, device=x.device)
     residual = _f32c(residual) if residual is not None else None
-    wsb = L.cpd_gather_gemm_workspace_bytes(m_out, cin, K, cout, algo)
+    wsb = L.cpd_gather_gemm_workspace_bytes(x.shape[0], m_out, cin, K, cout, algo, int(x_split is not None))
     ws = _ws(wsb, x.device) if wsb else None
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    _lib.check(L.cpd_gather_gemm(_ptr(x), x.shape[0], cin, _ptr(w), K, cout, _ptr(nbr), m_out, _ptr(bias), _ptr(scale),
-                                 _ptr(shift), _ptr(residual), int(bool(relu)), _ptr(stats), _ptr(y), int(algo),
+    _lib.check(L.cpd_gather_gemm(_ptr(x), _ptr(x_split), x.shape[0], cin, _ptr(w), K, cout, _ptr(nbr), m_out, _ptr(bias),
+                                 _ptr(scale), _ptr(shift), _ptr(residual), int(bool(relu)), _ptr(stats), _ptr(y), int(algo),
                                  _ptr(ws), wsb, _stream()), "cpd_gather_gemm")
     if PROFILE is not None:
         e1.record()
@@ -201,8 +216,9 @@ def gather_gemm(x, w, nbr, bias=None, scale=None, shift=None, residual=None, rel
     return y
 
 
-def gather_wgrad(x, dy, nbr, want_bias=False, algo=ALGO_AUTO, tap_major=False):
-    """dw (cout, K, cin), dbias (cout,) | None.  tap_major: nbr is the transposed (K, m_out) table."""
+def gather_wgrad(x, dy, nbr, want_bias=False, algo=ALGO_AUTO, tap_major=False, x_split=None, dy_split=None):
+    """dw (cout, K, cin), dbias (cout,) | None.  tap_major: nbr is the transposed (K, m_out) table.
+    x_split / dy_split: split_rows() images the caller already has."""
     _need_cuda(x, dy, nbr)
     L = _lib.lib()
     x, dy = _f32c(x), _f32c(dy)
@@ -210,13 +226,15 @@ def gather_wgrad(x, dy, nbr, want_bias=False, algo=ALGO_AUTO, tap_major=False):
     assert nbr.is_contiguous() and nbr.shape[1 if tap_major else 0] == dy.shape[0]
     dw = torch.empty((cout, K, cin), dtype=torch.float32, device=x.device)
     db = torch.empty((cout,), dtype=torch.float32, device=x.device) if want_bias else None
-    wsb = L.cpd_gather_wgrad_workspace_bytes(dy.shape[0], cin, K, cout)
+    wsb = 0 if algo == ALGO_SIMT else L.cpd_gather_wgrad_workspace_bytes(x.shape[0], dy.shape[0], cin, K, cout,
+                                                                          int(x_split is not None), int(dy_split is not None))
     ws = _ws(wsb, x.device) if wsb else None
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    _lib.check(L.cpd_gather_wgrad(_ptr(x), x.shape[0], cin, _ptr(dy), dy.shape[0], cout, _ptr(nbr), int(bool(tap_major)), K,
-                                  _ptr(dw), _ptr(db), int(algo), _ptr(ws), wsb, _stream()), "cpd_gather_wgrad")
+    _lib.check(L.cpd_gather_wgrad(_ptr(x), _ptr(x_split), x.shape[0], cin, _ptr(dy), _ptr(dy_split), dy.shape[0], cout, _ptr(nbr),
+                                  int(bool(tap_major)), K, _ptr(dw), _ptr(db), int(algo), _ptr(ws), wsb, _stream()),
+               "cpd_gather_wgrad")
     if PROFILE is not None:
         e1.record()
         PROFILE.append((e0, e1, dict(kind="gather_wgrad", m_in=x.shape[0], m_out=dy.shape[0], cin=cin, cout=cout, K=K, nbr=nbr,

@@ -128,19 +128,32 @@ CPD_API int32_t cpd_rulebook_strided_tables(const int32_t *in_coords, int64_t m_
  * --------------------------------------------------------------------------------- */
 enum cpd_gemm_algo { CPD_ALGO_AUTO = 0, CPD_ALGO_SIMT = 1, CPD_ALGO_TCGEN05 = 2 };
 
-CPD_API int32_t cpd_gather_gemm(const float *x, int64_t m_in, int32_t cin, const float *w, int32_t K, int32_t cout,
-                        const int32_t *nbr, int64_t m_out, const float *bias, const float *scale,
-                        const float *shift, const float *residual, int32_t relu, float *stats, float *y,
-                        int32_t algo, void *ws, size_t ws_bytes, cpd_stream_t stream);
-CPD_API size_t cpd_gather_gemm_workspace_bytes(int64_t m_out, int32_t cin, int32_t K, int32_t cout, int32_t algo);
+/* Split-row image, the operand format of the tcgen05 kernels: xs (m, 2, c) bf16, row i = [hi(c) | lo(c)],
+ * hi = RN_bf16(x), lo = RN_bf16(x - hi); same byte size and row pitch (4 c bytes) as x.  c % 8 == 0.
+ * cpd_gather_gemm / cpd_gather_wgrad build the images they need in their workspace unless the caller
+ * passes one it already has (x_split / dy_split != NULL): forward and weight-gradient share the image
+ * of x, input-gradient and weight-gradient share the image of dy. */
+CPD_API int32_t cpd_split_rows(const float *x, int64_t m, int32_t c, void *xs, cpd_stream_t stream);
+
+/* x_split (NULL ok): split-row image of x (cpd_split_rows); have_x_split tells the workspace query
+ * whether the call will pass one. */
+CPD_API int32_t cpd_gather_gemm(const float *x, const void *x_split, int64_t m_in, int32_t cin, const float *w,
+                        int32_t K, int32_t cout, const int32_t *nbr, int64_t m_out, const float *bias,
+                        const float *scale, const float *shift, const float *residual, int32_t relu,
+                        float *stats, float *y, int32_t algo, void *ws, size_t ws_bytes, cpd_stream_t stream);
+CPD_API size_t cpd_gather_gemm_workspace_bytes(int64_t m_in, int64_t m_out, int32_t cin, int32_t K, int32_t cout,
+                                       int32_t algo, int32_t have_x_split);
 
 /* Weight-gradient: dw[co, k, ci] = sum_o dy[o, co] * x[nbr[o, k], ci]; dw is overwritten.
  * dbias (NULL ok): dbias[co] = sum_o dy[o, co].  nbr_tap_major != 0: nbr is the transposed
- * (K, m_out) table (coalesced per-tap scans; what the tcgen05 kernel prefers). */
-CPD_API int32_t cpd_gather_wgrad(const float *x, int64_t m_in, int32_t cin, const float *dy, int64_t m_out,
-                         int32_t cout, const int32_t *nbr, int32_t nbr_tap_major, int32_t K, float *dw,
-                         float *dbias, int32_t algo, void *ws, size_t ws_bytes, cpd_stream_t stream);
-CPD_API size_t cpd_gather_wgrad_workspace_bytes(int64_t m_out, int32_t cin, int32_t K, int32_t cout);
+ * (K, m_out) table (coalesced per-tap scans; what the tcgen05 kernel prefers).
+ * x_split / dy_split (NULL ok): split-row images of x / dy. */
+CPD_API int32_t cpd_gather_wgrad(const float *x, const void *x_split, int64_t m_in, int32_t cin, const float *dy,
+                         const void *dy_split, int64_t m_out, int32_t cout, const int32_t *nbr,
+                         int32_t nbr_tap_major, int32_t K, float *dw, float *dbias, int32_t algo, void *ws,
+                         size_t ws_bytes, cpd_stream_t stream);
+CPD_API size_t cpd_gather_wgrad_workspace_bytes(int64_t m_in, int64_t m_out, int32_t cin, int32_t K, int32_t cout,
+                                        int32_t have_x_split, int32_t have_dy_split);
 
 /* Training-mode BatchNorm on a row matrix x (m, c), fused with ReLU and the residual add: replaces
  * nn.BatchNorm1d/2d + nn.ReLU (+ `out + identity`) after the convolutions
