@@ -11,29 +11,37 @@
 // k-block, a 128-channel layer spends two k-blocks per tap.  W (cout, K, cin) is already contiguous
 // along f, so the B operand of k-block kb is simply W[:, 64 kb : 64 kb + 64].
 //
-// One CTA = 128 output rows x BN output channels, accumulators in TMEM.
+// PERSISTENT, warp-specialised: one CTA per SM walks the (128-row x BN-channel) output tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ...; the operand pipeline never drains between tiles and the
+// epilogue of tile i overlaps the main loop of tile i+1 (double-buffered TMEM accumulators).
 //   weight_split_kernel (one tiny launch before the GEMM): W -> bf16 hi / lo images stored in
 //              global memory ALREADY in the swizzled shared-memory tile layout, one contiguous
 //              [hi | lo] block of 2 * BN * 128 bytes per (k-block, cout tile).
-//   warp 9     per k-block ONE cp.async.bulk (TMA engine, no tensor map needed because the image
-//              is pre-swizzled) brings the B tile in, completing on the stage's full barrier.
-//   warps 0-7  producers: gather A rows from the split-row image of x (split.cu: every row is split
+//   warp 13    loader: per k-block ONE cp.async.bulk (TMA engine; no tensor map needed because the
+//              image is pre-swizzled) brings the B tile in; per tile one more bulk copy prefetches
+//              the NEXT tile's [128 x K] slice of the neighbour table into a double-buffered
+//              shared-memory copy.
+//   warps 4-11 producers: gather A rows from the split-row image of x (split.cu: every row is split
 //              into bf16 hi | lo ONCE per layer, not once per rulebook pair) with 16-byte cp.async
 //              straight into the canonical K-major SWIZZLE_128B layout that UMMA descriptors address:
 //              no register staging, no conversion work in the loop, missing neighbours zero-filled by
-//              the copy itself (src-size 0), STAGES-1 k-blocks in flight per thread.  Completed groups
-//              are handed over with cp.async.wait_group + fence.proxy.async + mbarrier arrive.
-//              k-blocks none of whose taps has a neighbour in the tile are skipped altogether.
-//   warp 8     allocates TMEM, then one elected lane issues per k-block 4 x 3
+//              the copy itself (src-size 0), STAGES-1 k-blocks (up to 4 x 32 KB) in flight per SM --
+//              the gather is L2-latency bound, so bytes in flight are what buys bandwidth.
+//              Each thread's copies signal the stage's mbarrier themselves when they land
+//              (cp.async.mbarrier.arrive.noinc): the producers never wait for data.  (A producer-side
+//              cp.async.wait_group + fence.proxy.async hand-over serialises the pipeline -- the proxy
+//              fence waits for ALL of the thread's copies in flight -- and ran 2x slower.)  The
+//              generic -> async proxy fence is executed by the MMA warp after it has observed the barrier.
+//   warp 12    allocates TMEM, then one elected lane issues per k-block 4 x 3
 //              tcgen05.mma.cta_group::1.kind::f16 (A_hi.B_hi + A_lo.B_hi + A_hi.B_lo, M=128,
-//              N=BN, K=16) and tcgen05.commit's the stage back.
-//   warps 0-7  epilogue: tcgen05.ld the accumulators (lane = row), + bias, stage through shared
-//              memory (padded rows, conflict-free), then coalesced float4 stores with the folded
-//              BatchNorm affine / residual / ReLU applied on the way out and per-channel
-//              sum / sum-of-squares taken from the staged tile.
+//              N=BN, K=16), tcgen05.commit's the stage back and, per tile, the accumulator over.
+//   warps 0-3  epilogue: tcgen05.ld the accumulators (lane = row), + bias, per-channel sum /
+//              sum-of-squares (training BatchNorm statistics: butterfly transpose-reduce across the
+//              warp, kept in registers across tiles, ONE atomic per column per warp at the end),
+//              folded-BatchNorm affine / residual / ReLU, 64-byte row segments stored directly.
 //
 // Why bf16x3: one bf16 product keeps 8 mantissa bits, far from the 1e-4 parity bar;
-// hi = RN(x), lo = RN(x - hi) restores ~2^-17 relative error per product (measured ~1e-5 on the
+// hi = RN(x), lo = RN(x - hi) restores ~2^-17 relative error per product (measured ~2e-5 on the
 // layer outputs, tools/tc_check.py) and moves half the shared-memory bytes of a 3xTF32 split --
 // and shared-memory bandwidth (operand stores + UMMA operand reads), not the tensor pipe, is what
 // bounds a 3-product emulation at M = N = 128.
@@ -45,26 +53,23 @@ using namespace tc;
 
 constexpr int BM = 128;       // UMMA M
 constexpr int BKE = 64;       // bf16 elements per k-block = 128 bytes = one swizzle row
-constexpr int NPW = 8;             // producer / epilogue warps (two per SM sub-partition, so their issue stalls overlap)
+constexpr int NEPI = 128;     // warps 0-3: epilogue (TMEM lane quarter = warp index)
+constexpr int NPW = 8;        // warps 4-11: producers
 constexpr int NPROD = NPW * 32;
-constexpr int NTHREADS = NPROD + 64;   // + MMA warp (warp NPW) + B-loader warp (warp NPW + 1)
+constexpr int MMA_WARP = (NEPI + NPROD) / 32;      // warp 12: MMA issuer, warp 13: loader
+constexpr int NTHREADS = NEPI + NPROD + 64;
 constexpr int RSTEP = NPROD / 8;   // row stride between the chunks one producer thread owns (8 x 16 B chunks per row)
 constexpr int A_V = BM / RSTEP;    // rows per producer thread per k-block
-constexpr int MAX_TAPS = 32;
-constexpr int MAX_KB = 512;        // k-blocks per tile (K * cin / 64)
+constexpr int MAX_TAPS = 27;
 
-__host__ __device__ constexpr int stages_for(int bn) { return bn >= 256 ? 2 : bn >= 128 ? 3 : 2; }
-__host__ __device__ constexpr int ctas_per_sm(int bn) { return bn <= 64 ? 2 : 1; }
 __host__ __device__ constexpr int stage_bytes(int bn) { return 2 * BM * 128 + 2 * bn * 128; }
-// TMEM accumulators per tile: n_main(bn) "main" ones (A_hi.B_hi, k-blocks dealt round-robin) + 1
-// "correction" one (A_lo.B_hi + A_hi.B_lo, ~2^-9 of the main magnitude).  The tensor core
-// truncates when it adds into the fp32 accumulator; with hundreds of adds into one accumulator
-// that bias becomes visible at the 1e-4 level.  Spreading the adds over separate accumulators and
-// summing them in fp32 registers in the epilogue cuts it for free (TMEM columns are idle).
-__host__ __device__ constexpr int n_main(int bn) { return bn <= 128 ? 2 : 1; }
+__host__ __device__ constexpr int stages_for(int bn) { return bn >= 256 ? 2 : bn >= 128 ? 3 : bn >= 32 ? 4 : 5; }
+// TMEM: per accumulator buffer one "main" (A_hi.B_hi) and one "correction" (A_lo.B_hi + A_hi.B_lo, ~2^-9 of
+// the main magnitude) accumulator of BN columns each; two buffers (tile i / tile i+1) when they fit in 512 columns.
+__host__ __device__ constexpr int acc_bufs(int bn) { return bn <= 128 ? 2 : 1; }
 __host__ __device__ constexpr int tmem_cols(int bn)
 {
-    int need = (n_main(bn) + 1) * bn, c = 32;
+    int need = acc_bufs(bn) * 2 * bn, c = 32;
     while (c < need) c <<= 1;
     return c;
 }
@@ -79,9 +84,9 @@ __host__ __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_
 
 struct TcArgs {
     const float *bias, *scale, *shift, *residual;
-    const uint8_t *xs;          // split-row image of x: row i = [hi(cin) | lo(cin)] bf16
+    const uint8_t *xs;          // split-row image of x: row i = [hi(cin) | lo(cin)] bf16 (split.cu)
     const uint8_t *wsplit;      // [k-block][cout tile][hi | lo][BN rows x 128 B, swizzled]
-    const int32_t *nbr;
+    const int32_t *nbr;         // (m_out, K)
     float *stats, *y;
     long long m_out;
     int cin, K, cout, relu;
@@ -109,248 +114,305 @@ __global__ void weight_split_kernel(const float *__restrict__ w, int cout, int K
     *reinterpret_cast<uint4 *>(base + (size_t)bn * 128 + off) = l;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(NTHREADS, ctas_per_sm(BN)) gather_gemm_tc_kernel(TcArgs a)
+// Sum x[0..31] of every lane across the 32 lanes of a warp: lane L returns the total of x[L] (31 shuffles).
+__device__ __forceinline__ float warp_transpose_reduce(float (&x)[32], int lane)
 {
-    constexpr int STAGES = stages_for(BN);
-    constexpr int NMAIN = n_main(BN);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = upper ? x[i] : x[i + off];
+            const float keep = upper ? x[i + off] : x[i];
+            x[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return x[0];
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
+{
+    constexpr int STAGES = stages_for(BN), ACC = acc_bufs(BN);
     constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE = stage_bytes(BN);
-    constexpr int OUT_LD = BN + 4;   // padded staging row (floats): conflict-free 16-byte stores
-    static_assert(BM * OUT_LD * 4 <= STAGES * STAGE, "epilogue staging must fit in the pipeline buffers");
     // fp32 accumulate (bit 4), bf16 A and B (bits 7, 10), K-major both, N >> 3, M >> 4
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    int32_t *nbr_s = reinterpret_cast<int32_t *>(tiles + STAGES * STAGE);          // [K][BM]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(nbr_s + a.K * BM);              // full[S], empty[S], accum
-    uint32_t *misc = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);         // [0] tmem base, [1] tap mask, [2] active k-blocks
-    uint16_t *kb_list = reinterpret_cast<uint16_t *>(misc + 4);                   // [n_kb] active k-block indices
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum_bar = smem_u32(bars + 2 * STAGES);
+    const int tbl_ints = BM * a.K;
+    int32_t *nbr_s = reinterpret_cast<int32_t *>(tiles + STAGES * STAGE);          // [2][BM][K]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(nbr_s + 2 * tbl_ints);          // full[S] empty[S] tbl_full[2] tbl_empty[2] acc_full[2] acc_empty[2]
+    uint32_t *misc = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 8);         // [0] tmem base
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * STAGES, tblf0 = empty0 + 8 * STAGES, tble0 = tblf0 + 16,
+                   accf0 = tble0 + 16, acce0 = accf0 + 16;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long row0 = (long long)blockIdx.x * BM;
-    const int n0 = blockIdx.y * BN;                    // output-channel tile (cout > 256 is split over grid.y)
     const int Kf = a.K * a.cin;
     const int n_kb = (Kf + BKE - 1) / BKE;
+    const int ntn = a.cout / BN;                                   // cout tiles (cout > 256 only)
+    const long long total_tiles = ((a.m_out + BM - 1) / BM) * ntn;
 
-    if (tid == 0) misc[1] = 0u;
-    if (warp == NPW) {
+    if (warp == MMA_WARP) {
         if (lane == 0) {
-            for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, NPW + 1); mbar_init(empty0 + 8 * s, 1); }
-            mbar_init(accum_bar, 1);
+            for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, NPROD + 1); mbar_init(empty0 + 8 * s, 1); }
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(tblf0 + 8 * b, 1); mbar_init(tble0 + 8 * b, NPW);
+                mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, NEPI / 32);
+            }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(misc)), "r"(tmem_cols(BN)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    __syncthreads();
-    if (tid < BM) {   // neighbour tile -> smem, and the set of taps that have any work in this tile
-        const long long row = row0 + tid;
-        uint32_t mine = 0u;
-        for (int k = 0; k < a.K; ++k) {
-            int32_t idx = row < a.m_out ? __ldg(a.nbr + row * a.K + k) : -1;
-            nbr_s[k * BM + tid] = idx;
-            if (idx >= 0) mine |= 1u << k;
-        }
-        mine = __reduce_or_sync(0xffffffffu, mine);
-        if (lane == 0 && mine) atomicOr(&misc[1], mine);
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = misc[0];
-    if (warp == 0) {   // ordered list of the k-blocks that touch at least one active tap
-        const uint32_t tap_mask = misc[1];
-        int cnt = 0;
-        for (int base = 0; base < n_kb; base += 32) {
-            const int kb = base + lane;
-            bool act = false;
-            if (kb < n_kb) {
-                const int t0 = (kb * BKE) / a.cin;
-                int t1 = (kb * BKE + BKE - 1) / a.cin;
-                if (t1 > a.K - 1) t1 = a.K - 1;
-                const uint32_t upto = t1 >= 31 ? 0xffffffffu : ((1u << (t1 + 1)) - 1u);
-                act = (tap_mask & upto & ~((1u << t0) - 1u)) != 0u;
-            }
-            const uint32_t b = __ballot_sync(0xffffffffu, act);
-            if (act) kb_list[cnt + __popc(b & ((1u << lane) - 1u))] = (uint16_t)kb;
-            cnt += __popc(b);
-        }
-        if (lane == 0) misc[2] = (uint32_t)cnt;
-    }
-    asm volatile("bar.sync 2, %0;" ::"n"(NTHREADS) : "memory");
-    const int n_iters = (int)misc[2];
 
-    if (warp < NPW) {
-        // ================= producers =================
-        const int c = tid & 7, r_base = tid >> 3;   // 16-byte smem chunk (8 channels), first row (rows r_base + RSTEP j)
-        uint32_t soff[A_V];                         // swizzled byte offsets of this thread's chunks (loop invariant)
+    if (warp < NEPI / 32) {
+        // ================= epilogue (warps 0-3; TMEM lanes 32 * warp .. + 31 = tile rows) =================
+        float st_acc[BN / 16];                      // running BatchNorm statistics: lane L < 16: sum of column 16 i + L; L >= 16: sum of squares
+#pragma unroll
+        for (int i = 0; i < BN / 16; ++i) st_acc[i] = 0.f;
+        int ti = 0;
+        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+            const int buf = ACC == 2 ? (ti & 1) : 0;
+            mbar_wait(accf0 + 8 * buf, ACC == 2 ? ((ti >> 1) & 1) : (ti & 1));
+            tc_fence_after();
+            const long long row = (t / ntn) * BM + warp * 32 + lane;
+            const int n0 = (int)(t % ntn) * BN;
+            const bool valid = row < a.m_out;
+            const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 2 * BN);
+#pragma unroll
+            for (int i = 0; i < BN / 16; ++i) {
+                uint32_t u[16], v[16];
+                tmem_ld16(tacc + (uint32_t)(16 * i), u);                 // main
+                tmem_ld16(tacc + (uint32_t)(BN + 16 * i), v);            // correction
+                if (i == BN / 16 - 1) {                                  // accumulator fully read: hand the buffer back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acce0 + 8 * buf);
+                }
+                float o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(u[j]) + __uint_as_float(v[j]);
+                const int cv = n0 + 16 * i;
+                if (a.bias) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 b = __ldg(reinterpret_cast<const float4 *>(a.bias + cv + 4 * q));
+                        o[4 * q] += b.x; o[4 * q + 1] += b.y; o[4 * q + 2] += b.z; o[4 * q + 3] += b.w;
+                    }
+                }
+                if (a.stats) {                                           // statistics of the pre-affine output
+                    float x[32];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { x[j] = valid ? o[j] : 0.f; x[16 + j] = x[j] * x[j]; }
+                    st_acc[i] += warp_transpose_reduce(x, lane);
+                }
+                if (valid) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float4 r = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                        if (a.scale) {
+                            const float4 sc = __ldg(reinterpret_cast<const float4 *>(a.scale + cv + 4 * q));
+                            const float4 sh = __ldg(reinterpret_cast<const float4 *>(a.shift + cv + 4 * q));
+                            r.x = fmaf(r.x, sc.x, sh.x); r.y = fmaf(r.y, sc.y, sh.y); r.z = fmaf(r.z, sc.z, sh.z); r.w = fmaf(r.w, sc.w, sh.w);
+                        }
+                        if (a.residual) {
+                            const float4 rs = __ldg(reinterpret_cast<const float4 *>(a.residual + row * a.cout + cv + 4 * q));
+                            r.x += rs.x; r.y += rs.y; r.z += rs.z; r.w += rs.w;
+                        }
+                        if (a.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+                        *reinterpret_cast<float4 *>(a.y + row * a.cout + cv + 4 * q) = r;
+                    }
+                }
+            }
+            if (a.stats && ntn > 1) {               // the cout tile changes from one tile to the next: flush per tile
+#pragma unroll
+                for (int i = 0; i < BN / 16; ++i) {
+                    atomicAdd(a.stats + (lane < 16 ? 0 : a.cout) + n0 + 16 * i + (lane & 15), st_acc[i]);
+                    st_acc[i] = 0.f;
+                }
+            }
+        }
+        if (a.stats && ntn == 1) {
+#pragma unroll
+            for (int i = 0; i < BN / 16; ++i) atomicAdd(a.stats + (lane < 16 ? 0 : a.cout) + 16 * i + (lane & 15), st_acc[i]);
+        }
+    } else if (warp < MMA_WARP) {
+        // ================= producers (warps 4-11) =================
+        const int ptid = tid - NEPI;
+        const int c = ptid & 7, r_base = ptid >> 3;   // 16-byte smem chunk (8 channels), first row (rows r_base + RSTEP j)
+        uint32_t soff[A_V];                           // swizzled byte offsets of this thread's chunks (loop invariant)
 #pragma unroll
         for (int j = 0; j < A_V; ++j) soff[j] = swz(r_base + RSTEP * j, c);
         const uint32_t tiles_u32 = smem_u32(tiles);
         const size_t row_bytes = (size_t)a.cin * 4;                // image row = hi(cin) | lo(cin) bf16
         const uint32_t lo_off = (uint32_t)a.cin * 2;
-        auto issue = [&](int it) {
-            const int s = it % STAGES;
-            mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
-            const int f = (int)kb_list[it] * BKE + c * 8;            // flattened (tap, channel) index of this thread's chunk
-            const int k = f / a.cin, ch = f - k * a.cin;
-            const bool k_ok = k < a.K;
-            const int32_t *nb = nbr_s + (k_ok ? k : 0) * BM + r_base;
-            const uint32_t dst = tiles_u32 + (uint32_t)(s * STAGE);
-            const uint8_t *col = a.xs + (size_t)ch * 2;
+        int g = 0, ti = 0;                            // k-blocks issued so far (all tiles), tiles started
+        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+            const long long row0 = (t / ntn) * BM;
+            const int tb = ti & 1;
+            mbar_wait(tblf0 + 8 * tb, (ti >> 1) & 1);                              // this tile's slice of the neighbour table has landed
+            const int32_t *tab = nbr_s + tb * tbl_ints + r_base * a.K;
+            int rows_left = (int)min((long long)BM, a.m_out - row0) - r_base;     // rows r_base + RSTEP j < rows of the tile
+            for (int kb = 0; kb < n_kb; ++kb, ++g) {
+                const int s = g % STAGES;
+                mbar_wait(empty0 + 8 * s, ((g / STAGES) & 1) ^ 1);
+                const int f = kb * BKE + c * 8;        // flattened (tap, channel) index of this thread's chunk
+                const int k = f / a.cin, ch = f - k * a.cin;
+                const bool k_ok = k < a.K;
+                const uint32_t dst = tiles_u32 + (uint32_t)(s * STAGE);
+                const uint8_t *col = a.xs + (size_t)ch * 2;
 #pragma unroll
-            for (int j = 0; j < A_V; ++j) {
-                const int32_t idx = k_ok ? nb[RSTEP * j] : -1;
-                const uint8_t *src = col + (size_t)(idx >= 0 ? idx : 0) * row_bytes;
-                const uint32_t sz = idx >= 0 ? 16u : 0u;                 // 0 -> the copy writes 16 zero bytes
-                cp_async16(dst + soff[j], src, sz);
-                cp_async16(dst + A_BYTES + soff[j], src + lo_off, sz);
-            }
-        };
-        constexpr int D = STAGES - 1;               // k-blocks in flight per thread
-        for (int it = 0; it < n_iters + D; ++it) {
-            if (it < n_iters) issue(it);
-            cp_async_commit();
-            if (it >= D) {
-                cp_async_wait<D>();                  // group it - D has landed
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full0 + 8 * ((it - D) % STAGES));      // one arrival per producer warp
-            }
-        }
-        // ================= epilogue =================
-        float *stage_out = reinterpret_cast<float *>(tiles);
-        if (n_iters > 0) {
-            mbar_wait(accum_bar, 0);
-            tc_fence_after();
-        }
-        // warp w may read TMEM lanes 32*(w%4)..+31; the two warps sharing a lane quarter split the columns
-        const int my_row = (warp & 3) * 32 + lane;
-        const int n_acc = n_iters == 0 ? 0 : (n_iters < NMAIN ? n_iters : NMAIN) + 1;   // mains in use + correction
-        constexpr int COLS_PER_GROUP = BN / (NPW / 4) >= 16 ? BN / (NPW / 4) : 16;
-        const int c_begin = (warp >> 2) * COLS_PER_GROUP;
-#pragma unroll
-        for (int cc = 0; cc < COLS_PER_GROUP; cc += 16) {
-            const int c0 = c_begin + cc;
-            if (c0 >= BN) break;
-            float v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0.f;
-            for (int acc = 0; acc < n_acc; ++acc) {
-                const int slot = acc == n_acc - 1 ? NMAIN : acc;                              // last one read = correction
-                const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(slot * BN + c0);
-                uint32_t u[16];
-                tmem_ld16(taddr, u);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(u[j]);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float4 o;
-                o.x = v[4 * q + 0]; o.y = v[4 * q + 1];
-                o.z = v[4 * q + 2]; o.w = v[4 * q + 3];
-                if (a.bias) {
-                    const float4 b = __ldg(reinterpret_cast<const float4 *>(a.bias + n0 + c0 + 4 * q));
-                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                for (int j = 0; j < A_V; ++j) {
+                    const int32_t idx = (k_ok && RSTEP * j < rows_left) ? tab[RSTEP * j * a.K + k] : -1;
+                    const uint8_t *src = col + (size_t)(idx >= 0 ? idx : 0) * row_bytes;
+                    const uint32_t sz = idx >= 0 ? 16u : 0u;             // 0 -> the copy writes 16 zero bytes
+                    cp_async16(dst + soff[j], src, sz);
+                    cp_async16(dst + A_BYTES + soff[j], src + lo_off, sz);
                 }
-                *reinterpret_cast<float4 *>(stage_out + my_row * OUT_LD + c0 + 4 * q) = o;
-            }
-        }
-        tc_fence_before();
-        asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
-        if (a.stats && tid < BN) {   // training-mode BatchNorm statistics of the pre-affine output
-            float s = 0.f, q = 0.f;
-            const int rows = (int)min((long long)BM, a.m_out - row0);
-            for (int r = 0; r < rows; ++r) { float t = stage_out[r * OUT_LD + tid]; s += t; q += t * t; }
-            atomicAdd(a.stats + n0 + tid, s);
-            atomicAdd(a.stats + a.cout + n0 + tid, q);
-        }
-        constexpr int V_PER_ROW = BN / 4;
-        for (int t = tid; t < BM * V_PER_ROW; t += NPROD) {
-            const int r = t / V_PER_ROW, cl = (t % V_PER_ROW) * 4, cv = n0 + cl;
-            const long long row = row0 + r;
-            if (row >= a.m_out) break;
-            float4 o = *reinterpret_cast<const float4 *>(stage_out + r * OUT_LD + cl);
-            if (a.scale) {
-                const float4 sc = __ldg(reinterpret_cast<const float4 *>(a.scale + cv));
-                const float4 sh = __ldg(reinterpret_cast<const float4 *>(a.shift + cv));
-                o.x = fmaf(o.x, sc.x, sh.x); o.y = fmaf(o.y, sc.y, sh.y); o.z = fmaf(o.z, sc.z, sh.z); o.w = fmaf(o.w, sc.w, sh.w);
-            }
-            if (a.residual) {
-                const float4 rs = __ldg(reinterpret_cast<const float4 *>(a.residual + row * a.cout + cv));
-                o.x += rs.x; o.y += rs.y; o.z += rs.z; o.w += rs.w;
-            }
-            if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            *reinterpret_cast<float4 *>(a.y + row * a.cout + cv) = o;
-        }
-    } else if (warp == NPW) {
-        // ================= MMA issuer =================
-        for (int it = 0; it < n_iters; ++it) {
-            const int s = it % STAGES;
-            mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t st = smem_u32(tiles + s * STAGE);
-                const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + A_BYTES);
-                const uint64_t b_hi = make_desc(st + 2 * A_BYTES), b_lo = make_desc(st + 2 * A_BYTES + B_BYTES);
-                const int rem = Kf - (int)kb_list[it] * BKE;                  // contraction elements left from this k-block on
-                const int k16n = rem >= BKE ? BKE / 16 : (rem + 15) / 16;
-                const uint32_t d_main = tmem_base + (uint32_t)((it % NMAIN) * BN), d_corr = tmem_base + (uint32_t)(NMAIN * BN);
-                for (int k16 = 0; k16 < k16n; ++k16) {
-                    const uint64_t adv = (uint64_t)((k16 * 32) >> 4);   // +32 bytes along K inside the swizzle row
-                    umma_bf16(d_main, a_hi + adv, b_hi + adv, IDESC, (it >= NMAIN || k16) ? 1u : 0u);
-                    umma_bf16(d_corr, a_lo + adv, b_hi + adv, IDESC, (it | k16) ? 1u : 0u);
-                    umma_bf16(d_corr, a_hi + adv, b_lo + adv, IDESC, 1u);
-                }
-                umma_commit(empty0 + 8 * s);            // frees the stage once these MMAs have read it
-                if (it == n_iters - 1) umma_commit(accum_bar);
+                cp_async_arrive_noinc(full0 + 8 * s);    // this thread's arrival fires when its copies above have landed
             }
             __syncwarp();
+            if (lane == 0) mbar_arrive(tble0 + 8 * tb);                            // table copy no longer needed by this warp
+        }
+        cp_async_wait_all();
+    } else if (warp == MMA_WARP) {
+        // ================= MMA issuer =================
+        // Issue rate matters as much as tensor time here (measured, tools/micro/mma_bench2.cu): one thread
+        // issues a tcgen05.mma every ~52 clk at best, an M=128 instruction needs max(N/2, (4096 + 32 N)/128)
+        // clk of tensor / operand-read time.  So: (1) for BN <= 128 the B tile [B_hi | B_lo] (contiguous in
+        // the stage) is ONE N = 2 BN operand: A_hi.[B_hi|B_lo] lands in [main | corr] with one instruction
+        // and A_lo.B_hi is added into corr -- 2 instructions per K step instead of 3; (2) descriptors are a
+        // constant plus the stage offset, the K loop is unrolled, and one elected lane runs the stream.
+        constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((BN <= 128 ? 2 * BN : BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        constexpr uint64_t DESC_HI = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+        const uint32_t tiles_u32 = smem_u32(tiles);
+        const int last_k16 = (Kf - (n_kb - 1) * BKE + 15) / 16;       // K steps of the last (possibly partial) k-block
+        int g = 0, ti = 0;
+        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+            const int buf = ACC == 2 ? (ti & 1) : 0;
+            mbar_wait(acce0 + 8 * buf, (ACC == 2 ? ((ti >> 1) & 1) : (ti & 1)) ^ 1);   // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_main = tmem_base + (uint32_t)(buf * 2 * BN), d_corr = d_main + (uint32_t)BN;
+            for (int kb = 0; kb < n_kb; ++kb, ++g) {
+                const int s = g % STAGES;
+                mbar_wait(full0 + 8 * s, (g / STAGES) & 1);
+                fence_async_smem();        // the producers' cp.async writes (generic proxy), observed through the barrier -> async proxy
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t a_hi = DESC_HI | (uint64_t)(((tiles_u32 + (uint32_t)(s * STAGE)) & 0x3FFFFu) >> 4);
+                    const uint64_t a_lo = a_hi + (A_BYTES >> 4), b_hi = a_hi + (2 * A_BYTES >> 4), b_lo = b_hi + (B_BYTES >> 4);
+                    const int k16n = kb == n_kb - 1 ? last_k16 : BKE / 16;
+#pragma unroll
+                    for (int k16 = 0; k16 < BKE / 16; ++k16) {
+                        if (k16 < k16n) {
+                            const uint64_t adv = (uint64_t)(k16 * 2);            // +32 bytes along K inside the swizzle row
+                            if (BN <= 128) {
+                                if (kb == 0 && k16 == 0) umma_bf16_set(d_main, a_hi, b_hi, IDESC2);
+                                else umma_bf16_acc(d_main, a_hi + adv, b_hi + adv, IDESC2);           // [main | corr] += A_hi.[B_hi | B_lo]
+                                umma_bf16_acc(d_corr, a_lo + adv, b_hi + adv, IDESC);                // corr += A_lo.B_hi
+                            } else {
+                                if (kb == 0 && k16 == 0) {
+                                    umma_bf16_set(d_main, a_hi, b_hi, IDESC);
+                                    umma_bf16_set(d_corr, a_lo, b_hi, IDESC);
+                                } else {
+                                    umma_bf16_acc(d_main, a_hi + adv, b_hi + adv, IDESC);
+                                    umma_bf16_acc(d_corr, a_lo + adv, b_hi + adv, IDESC);
+                                }
+                                umma_bf16_acc(d_corr, a_hi + adv, b_lo + adv, IDESC);
+                            }
+                        }
+                    }
+                    umma_commit(empty0 + 8 * s);            // frees the stage once these MMAs have read it
+                    if (kb == n_kb - 1) umma_commit(accf0 + 8 * buf);
+                }
+                __syncwarp();
+            }
         }
         tc_fence_before();
     } else {
-        // ================= B loader: one bulk copy of the pre-swizzled [hi | lo] weight tile per k-block =================
-        const size_t tile_bytes = (size_t)(2 * B_BYTES);
-        const int ntiles = a.cout / BN;
-        for (int it = 0; it < n_iters; ++it) {
-            const int s = it % STAGES;
-            if (lane == 0) {
-                mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
-                const uint8_t *src = a.wsplit + ((size_t)kb_list[it] * ntiles + blockIdx.y) * tile_bytes;
-                mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)tile_bytes);
-                bulk_copy_g2s(smem_u32(tiles + s * STAGE + 2 * A_BYTES), src, (uint32_t)tile_bytes, full0 + 8 * s);
+        // ================= loader: B tiles + neighbour-table slices, all by bulk copy =================
+        const uint32_t tile_bytes = (uint32_t)(2 * B_BYTES);
+        auto load_table = [&](long long t, int tb) {          // rows of tile t -> nbr_s[tb]
+            const long long row0 = (t / ntn) * BM;
+            const int rows = (int)min((long long)BM, a.m_out - row0);
+            const int32_t *src = a.nbr + row0 * a.K;
+            int32_t *dst = nbr_s + tb * tbl_ints;
+            if (rows == BM) {                                  // BM * K * 4 bytes: a multiple of 16, 16-byte aligned source
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(tblf0 + 8 * tb, (uint32_t)(tbl_ints * 4));
+                    bulk_copy_g2s(smem_u32(dst), src, (uint32_t)(tbl_ints * 4), tblf0 + 8 * tb);
+                }
+            } else {                                           // ragged last tile: plain copy by the warp
+                for (int e = lane; e < rows * a.K; e += 32) dst[e] = __ldg(src + e);
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tblf0 + 8 * tb);
             }
-            __syncwarp();
+        };
+        if ((long long)blockIdx.x < total_tiles) load_table(blockIdx.x, 0);
+        int g = 0, ti = 0;
+        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+            const long long t_next = t + gridDim.x;
+            if (t_next < total_tiles) {
+                const int tbn = (ti + 1) & 1;
+                mbar_wait(tble0 + 8 * tbn, (((ti + 1) >> 1) & 1) ^ 1);             // producers are done with the tile that used this buffer
+                load_table(t_next, tbn);
+            }
+            const int nt = (int)(t % ntn);
+            for (int kb = 0; kb < n_kb; ++kb, ++g) {
+                const int s = g % STAGES;
+                if (lane == 0) {
+                    mbar_wait(empty0 + 8 * s, ((g / STAGES) & 1) ^ 1);
+                    const uint8_t *src = a.wsplit + ((size_t)kb * ntn + nt) * (size_t)tile_bytes;
+                    mbar_arrive_expect_tx(full0 + 8 * s, tile_bytes);
+                    bulk_copy_g2s(smem_u32(tiles + s * STAGE + 2 * A_BYTES), src, tile_bytes, full0 + 8 * s);
+                }
+                __syncwarp();
+            }
         }
     }
     __syncthreads();
-    if (warp == NPW) {
+    if (warp == MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols(BN)));
     }
 }
 
 template <int BN>
-size_t smem_bytes(int K, int n_kb)
+size_t smem_bytes(int K)
 {
-    return 1024 + (size_t)stages_for(BN) * stage_bytes(BN) + (size_t)K * BM * 4 + (2 * stages_for(BN) + 1) * 8 + 4 * 4 +
-           (size_t)((n_kb + 7) / 8 * 8) * 2;
+    return 1024 + (size_t)stages_for(BN) * stage_bytes(BN) + (size_t)2 * K * BM * 4 + (2 * stages_for(BN) + 8) * 8 + 16;
+}
+
+int num_sms()
+{
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
 }
 
 template <int BN>
-int32_t launch_tc(const TcArgs &a, int n_kb, cudaStream_t stream)
+int32_t launch_tc(const TcArgs &a, cudaStream_t stream)
 {
+    static_assert(stages_for(BN) * stage_bytes(BN) + 2 * MAX_TAPS * BM * 4 + 1024 + 256 <= 227 * 1024, "shared memory budget");
     static bool configured = false;
     if (!configured) {
-        CPD_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem_bytes<BN>(MAX_TAPS, MAX_KB)));
+        CPD_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN>(MAX_TAPS)));
         configured = true;
     }
-    dim3 grid((unsigned)div_up(a.m_out, BM), (unsigned)(a.cout / BN));
-    gather_gemm_tc_kernel<BN><<<grid, NTHREADS, smem_bytes<BN>(a.K, n_kb), stream>>>(a);
+    const long long tiles = div_up(a.m_out, BM) * (a.cout / BN);
+    const unsigned grid = (unsigned)(tiles < num_sms() ? tiles : num_sms());
+    gather_gemm_tc_kernel<BN><<<grid, NTHREADS, smem_bytes<BN>(a.K), stream>>>(a);
     count_launch();
     return launch_status("cpd_gather_gemm[tcgen05]");
 }
@@ -361,7 +423,7 @@ inline int bn_for(int cout) { return cout >= 256 ? 256 : cout; }
 
 bool gather_gemm_tc_supported(int32_t cin, int32_t K, int32_t cout)
 {
-    return cin % 8 == 0 && cin >= 8 && K <= MAX_TAPS && (long long)K * cin <= (long long)MAX_KB * BKE &&
+    return cin % 8 == 0 && cin >= 8 && K <= MAX_TAPS &&
            (cout == 16 || cout == 32 || cout == 64 || cout == 128 || (cout >= 256 && cout % 256 == 0 && cout <= 2048));
 }
 
@@ -378,7 +440,7 @@ int32_t gather_gemm_tc(const void *xs, int32_t cin, const float *w, int32_t K, i
 {
     CPD_REQUIRE(gather_gemm_tc_supported(cin, K, cout), CPD_ERR_UNSUPPORTED, "tcgen05 gather-GEMM: unsupported shape");
     CPD_REQUIRE((((uintptr_t)xs | (uintptr_t)w | (uintptr_t)y | (uintptr_t)bias | (uintptr_t)scale | (uintptr_t)shift |
-                  (uintptr_t)residual) & 15) == 0, CPD_ERR_MISALIGNED, "tcgen05 gather-GEMM: pointers must be 16-byte aligned");
+                  (uintptr_t)residual | (uintptr_t)nbr) & 15) == 0, CPD_ERR_MISALIGNED, "tcgen05 gather-GEMM: pointers must be 16-byte aligned");
     CPD_REQUIRE(ws && ws_bytes >= gather_gemm_tc_workspace(cin, K, cout), CPD_ERR_WORKSPACE, "tcgen05 gather-GEMM: workspace too small");
     uint8_t *wsplit = reinterpret_cast<uint8_t *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     const int Kf = K * cin, n_kb = (int)div_up(Kf, BKE), bn = bn_for(cout);
@@ -387,11 +449,11 @@ int32_t gather_gemm_tc(const void *xs, int32_t cin, const float *w, int32_t K, i
     count_launch();
     TcArgs a{bias, scale, shift, residual, reinterpret_cast<const uint8_t *>(xs), wsplit, nbr, stats, y, m_out, cin, K, cout, relu};
     switch (cout) {
-        case 16: return launch_tc<16>(a, n_kb, stream);
-        case 32: return launch_tc<32>(a, n_kb, stream);
-        case 64: return launch_tc<64>(a, n_kb, stream);
-        case 128: return launch_tc<128>(a, n_kb, stream);
-        default: return launch_tc<256>(a, n_kb, stream);
+        case 16: return launch_tc<16>(a, stream);
+        case 32: return launch_tc<32>(a, stream);
+        case 64: return launch_tc<64>(a, stream);
+        case 128: return launch_tc<128>(a, stream);
+        default: return launch_tc<256>(a, stream);
     }
 }
 

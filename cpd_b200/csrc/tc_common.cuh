@@ -47,6 +47,25 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc),
         "r"(idesc), "r"(accumulate) : "memory");
 }
+// One lane of a converged warp (the form the compiler turns into a single uniform branch around the UMMA stream;
+// `lane == 0` makes it wrap every tcgen05.mma in an elect / broadcast loop).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+    return p != 0;
+}
+// accumulate variants without the predicate register dance
+__device__ __forceinline__ void umma_bf16_acc(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+                 "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_set(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+                 "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -110,6 +129,12 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gmem_s
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// mbarrier arrival triggered when all prior cp.async of this thread have completed (counted in the barrier's init count)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols)
 {

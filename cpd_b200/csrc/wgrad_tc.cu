@@ -37,7 +37,6 @@ constexpr int WINR = 128;        // rows per neighbour-table window (4 k-blocks)
 constexpr int NPW = 8;            // producer / epilogue warps
 constexpr int NPROD = NPW * 32;
 constexpr int NTHREADS = NPROD + 32;
-constexpr uint32_t END_MARK = 0xffffffffu;
 constexpr int MAX_T = 32;        // taps per group (cin = 8 -> 32 taps in N = 256)
 constexpr int MAX_ROWS_PER_CTA = 4096;   // = 256 K-steps accumulated in one TMEM accumulator (bounds the truncation bias)
 
@@ -70,7 +69,7 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 }
 
 struct WgArgs {
-    const uint8_t *xs, *dys;     // split-row images: row i = [hi(c) | lo(c)] bf16
+    const uint8_t *xs, *dys;     // split-row images: row i = [hi(c) | lo(c)] bf16 (split.cu)
     const int32_t *nbr_t;        // tap-major table (K, m_out)
     float *dw;
     long long m_out;
@@ -107,12 +106,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
 
     if (warp == NPW) {
         if (lane == 0) {
-            for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, NPW); mbar_init(empty0 + 8 * s, 1); }
+            for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, NPROD); mbar_init(empty0 + 8 * s, 1); }
             mbar_init(accum_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
         tmem_alloc(smem_u32(misc), w_tmem_cols(BN));
+    }
+    if (warp < NPW) {
+        // Zero all operand stages once: columns beyond cout / (T*cin) are never written again.
+        for (int e = tid; e < STAGES * STAGE / 16; e += NPROD) reinterpret_cast<float4 *>(tiles)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        fence_async_smem();                          // generic-proxy zeros -> visible to the tensor core's async-proxy reads
     }
     tc_fence_before();
     __syncthreads();
@@ -120,8 +124,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
     const uint32_t tmem_base = misc[0];
 
     if (warp < NPW) {
-        // Zero all operand stages once: columns beyond cout / (T*cin) are never written again.
-        for (int e = tid; e < STAGES * STAGE / 16; e += NPROD) reinterpret_cast<float4 *>(tiles)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
         // loop-invariant mapping.  A: e = tid + 256 j over 32 x (AM/8) 16-byte chunks.
         uint32_t a_off[A_V];
         int a_row[A_V], a_col[A_V];
@@ -190,14 +192,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
                 }
             }
         };
-        auto complete = [&](int blk) {                                    // this thread's copies of block blk have landed
-            const int s = blk % STAGES;
-            const int nvalid = (int)min((long long)KB, r_end - (r_begin + (long long)blk * KB));
-            if (tid == 0) info[s] = (uint32_t)((nvalid + 15) / 16);
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full0 + 8 * s);      // one arrival per producer warp
-        };
         // before block `blk` is ISSUED its window's table must be published; windows are 4 blocks long
         auto prepare = [&](int blk) {
             if (blk % (WINR / KB) != 0 || blk >= n_blocks) return;
@@ -209,25 +203,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
             if (next < r_end) fetch_window(next);
         };
         fetch_window(r_begin);
-        asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");     // tiles zeroed
-        constexpr int D = STAGES - 1;                                  // k-blocks in flight per thread
-        for (int blk = 0; blk < n_blocks + D; ++blk) {
-            if (blk < n_blocks) { prepare(blk); issue(blk); }
-            cp_async_commit();
-            if (blk >= D) {
-                cp_async_wait<D>();
-                complete(blk - D);
-            }
+        // Each thread's copies signal the stage's mbarrier themselves when they land (cp.async.mbarrier.arrive.noinc):
+        // the producers never wait for data, only for a free stage.  The generic -> async proxy fence is executed by
+        // the MMA warp after it has observed the barrier (a producer-side wait_group + fence.proxy.async hand-over
+        // serialises the pipeline: the proxy fence waits for all of the thread's copies in flight).
+        for (int blk = 0; blk < n_blocks; ++blk) {
+            prepare(blk);
+            issue(blk);
+            cp_async_arrive_noinc(full0 + 8 * (blk % STAGES));
         }
-        const int it = n_blocks;
-        // ---- end marker, then epilogue ----
-        {
-            const int s = it % STAGES;
-            mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
-            if (tid == 0) info[s] = END_MARK;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full0 + 8 * s);      // barrier counts one arrival per producer warp
-        }
+        cp_async_wait_all();
+        // ---- epilogue ----
         if (n_blocks > 0) {
             mbar_wait(accum_bar, 0);
             tc_fence_after();
@@ -259,11 +245,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
     } else {
         // ================= MMA issuer =================
         int it = 0;
-        for (;; ++it) {
+        for (; it < n_blocks; ++it) {
             const int s = it % STAGES;
             mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
-            const uint32_t k16n = *reinterpret_cast<volatile uint32_t *>(&info[s]);
-            if (k16n == END_MARK) break;
+            const int nvalid = (int)min((long long)KB, r_end - (r_begin + (long long)it * KB));
+            const uint32_t k16n = (uint32_t)((nvalid + 15) / 16);
+            fence_async_smem();        // producers' cp.async / zero-fill writes (generic proxy), observed through the barrier -> async proxy
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t st = smem_u32(tiles + s * STAGE);

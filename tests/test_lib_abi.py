@@ -29,12 +29,16 @@ def test_header_symbols_exported_and_bound():
     assert L.cpd_nms_workspace_bytes(500) >= 500 * 8 * 8
     assert L.cpd_coord_hash_bytes(1000) >= 2 * 1000 * 8
     assert L.cpd_voxelize_workspace_bytes(1000, 1, 5, 1000) > 0
+    # tcgen05 workspaces: weight image (+ split-row images unless the caller brings them)
+    assert L.cpd_gather_gemm_workspace_bytes(1000, 1000, 32, 27, 32, 0, 0) >= 1000 * 32 * 4 + 14 * 32 * 256
+    assert L.cpd_gather_gemm_workspace_bytes(1000, 1000, 32, 27, 32, 0, 1) < 1000 * 32 * 4
+    assert L.cpd_gather_wgrad_workspace_bytes(1000, 900, 32, 27, 64, 0, 0) >= 1000 * 32 * 4 + 900 * 64 * 4
 
 
 def test_bad_arguments_return_status_not_exit():
     from cpd_b200 import _lib
     L = _lib.lib()
-    st = L.cpd_gather_gemm(None, 0, 4, None, 27, 4, None, 10, None, None, None, None, 0, None, None, 0, None, 0, None)
+    st = L.cpd_gather_gemm(None, None, 0, 4, None, 27, 4, None, 10, None, None, None, None, 0, None, None, 0, None, 0, None)
     assert st == -1 and b"null" in L.cpd_last_error_string()
     with pytest.raises(_lib.CpdError):
         _lib.check(st, "cpd_gather_gemm")
