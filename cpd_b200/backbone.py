@@ -123,18 +123,48 @@ class _Backbone8xBase(nn.Module):
 
     SORT_INPUT = True   # process the tower in ascending linear-key order (see _run_tower)
 
-    def _run_tower(self, sfx, feats, coords, batch_size, with_out):
+    def _sorted_order(self, coords):
+        # The voxelizer emits rows in first-appearance (i.e. shuffled) order.  A sparse tensor is a set, so the
+        # tower may visit it in any order: ascending ((b*D+z)*H+y)*W+x -- the order every strided conv already
+        # produces -- makes each 128-row tile spatially compact, so gathers hit L2/L1 and empty taps are skipped.
+        d, h, w = self.sparse_shape
+        c64 = coords.long()
+        key = ((c64[:, 0] * d + c64[:, 1]) * h + c64[:, 2]) * w + c64[:, 3]
+        perm = torch.argsort(key)
+        return perm, coords.index_select(0, perm).contiguous()
+
+    def plan_tower(self, sfx, coords, batch_size, with_out):
+        """Everything of a tower that depends on the voxel COORDINATES only: the visiting order and the whole rulebook
+        chain (spconv's indice_dict), built by walking the tower's convolutions without features.  All data-dependent
+        sizes -- hence all host syncs of the sparse path -- live here, so a plan can be made one step ahead on a side
+        stream (CPDHotPathDetector.prepare) and the forward pass itself never waits for the device."""
         coords = coords.int() if coords.dtype != torch.int32 else coords
+        perm = None
         if self.SORT_INPUT and coords.shape[0] > 0:
-            # The voxelizer emits rows in first-appearance (i.e. shuffled) order.  A sparse tensor is a set, so the
-            # tower may visit it in any order: ascending ((b*D+z)*H+y)*W+x -- the order every strided conv already
-            # produces -- makes each 128-row tile spatially compact, so gathers hit L2/L1 and empty taps are skipped.
-            d, h, w = self.sparse_shape
-            c64 = coords.long()
-            key = ((c64[:, 0] * d + c64[:, 1]) * h + c64[:, 2]) * w + c64[:, 3]
-            perm = torch.argsort(key)
-            feats, coords = feats.index_select(0, perm), coords.index_select(0, perm).contiguous()
-        x = sp.SparseConvTensor(feats, coords, self.sparse_shape, batch_size)
+            perm, coords = self._sorted_order(coords)
+        x = sp.SparseConvTensor(None, coords, self.sparse_shape, batch_size)
+        names = ["conv_input", "conv1", "conv2", "conv3", "conv4"]
+        seqs = [getattr(self, n + sfx) for n in names] + ([self.conv_out] if with_out else [])
+        for seq in seqs:
+            for m in seq.modules():                   # registration order == execution order in these towers
+                if isinstance(m, sp.SparseConvolution):
+                    rb, out_hash = m.get_rulebook(x)
+                    if rb.nbr_fwd.shape[1] > 1:
+                        rb.nbr_fwd_t                  # transposed table for the weight-gradient kernel
+                    x = m._wrap_output(x, rb, out_hash, None)
+        return dict(perm=perm, coords=coords, indice_dict=x.indice_dict)
+
+    def _run_tower(self, sfx, feats, coords, batch_size, with_out, plan=None):
+        coords = coords.int() if coords.dtype != torch.int32 else coords
+        indice_dict = None
+        if plan is not None:
+            coords, indice_dict = plan["coords"], plan["indice_dict"]
+            if plan["perm"] is not None:
+                feats = feats.index_select(0, plan["perm"])
+        elif self.SORT_INPUT and coords.shape[0] > 0:
+            perm, coords = self._sorted_order(coords)
+            feats = feats.index_select(0, perm)
+        x = sp.SparseConvTensor(feats, coords, self.sparse_shape, batch_size, indice_dict=indice_dict)
         x = getattr(self, "conv_input" + sfx)(x)
         c1 = getattr(self, "conv1" + sfx)(x)
         c2 = getattr(self, "conv2" + sfx)(c1)
@@ -154,11 +184,13 @@ class VoxelResBackBone8x(_Backbone8xBase):
 
     def forward(self, batch_dict):
         bs = batch_dict["batch_size"]
-        out, ms = self._run_tower("", batch_dict["voxel_features"], batch_dict["voxel_coords"], bs, True)
+        out, ms = self._run_tower("", batch_dict["voxel_features"], batch_dict["voxel_coords"], bs, True,
+                                  plan=batch_dict.get("tower_plan"))
         batch_dict.update({"encoded_spconv_tensor": out, "encoded_spconv_tensor_stride": 8,
                            "multi_scale_3d_features": ms, "multi_scale_3d_strides": dict(self._STRIDES)})
         if self.training and self.model_cfg.get("MM", False):
-            _, ms2 = self._run_tower("_2", batch_dict["voxel_features1"], batch_dict["voxel_coords1"], bs, False)
+            _, ms2 = self._run_tower("_2", batch_dict["voxel_features1"], batch_dict["voxel_coords1"], bs, False,
+                                     plan=batch_dict.get("tower_plan1"))
             batch_dict.update({"encoded_spconv_tensor_stride_mm": 8, "multi_scale_3d_features_mm": ms2,
                                "multi_scale_3d_strides": dict(self._STRIDES)})
         return batch_dict

@@ -357,7 +357,7 @@ extern "C" int32_t cpd_gather_gemm(const float *x, const void *x_split, int64_t 
         CPD_REQUIRE(ws && ws_bytes >= need, CPD_ERR_WORKSPACE, "cpd_gather_gemm: workspace too small (cpd_gather_gemm_workspace_bytes)");
         tc = true;
     } else if (algo == CPD_ALGO_AUTO) {
-        static const int min_cin = getenv("CPD_TC_MIN_CIN") ? atoi(getenv("CPD_TC_MIN_CIN")) : 16;   // tuning knob
+        static const int min_cin = getenv("CPD_TC_MIN_CIN") ? atoi(getenv("CPD_TC_MIN_CIN")) : 8;   // tuning knob
         tc = gather_gemm_tc_supported(cin, K, cout) && cin >= min_cin && ws && ws_bytes >= need;
     }
     if (tc) {
@@ -373,6 +373,7 @@ extern "C" int32_t cpd_gather_gemm(const float *x, const void *x_split, int64_t 
         return gather_gemm_tc(xs, cin, w, K, cout, nbr, m_out, bias, scale, shift, residual, relu, stats, y, p, left, stream);
     }
     CPD_REQUIRE(x, CPD_ERR_BAD_ARG, "cpd_gather_gemm: the SIMT kernel needs the fp32 rows");
+    if (stats) CPD_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)cout, stream));
     Epilogue ep{bias, scale, shift, residual, stats, relu};
     if (cout > 32) launch_gg<64, 64, 4, 4>(x, cin, w, K, cout, nbr, m_out, ep, y, stream);
     else if (cout > 16) launch_gg<128, 32, 4, 4>(x, cin, w, K, cout, nbr, m_out, ep, y, stream);

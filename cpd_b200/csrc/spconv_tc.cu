@@ -93,9 +93,12 @@ struct TcArgs {
 };
 
 // W (cout, Kf) fp32 -> pre-swizzled bf16 hi / lo tile images.  One thread per 16-byte output chunk.
-__global__ void weight_split_kernel(const float *__restrict__ w, int cout, int Kf, int n_kb, int bn, uint8_t *__restrict__ out)
+// Also clears the (2, cout) BatchNorm statistics accumulators of the GEMM that follows on the stream.
+__global__ void weight_split_kernel(const float *__restrict__ w, int cout, int Kf, int n_kb, int bn, uint8_t *__restrict__ out,
+                                    float *__restrict__ stats)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (stats && t < 2 * cout) stats[t] = 0.f;
     if (t >= (long long)n_kb * cout * 8) return;
     const int c = (int)(t & 7);
     const int n = (int)((t >> 3) % cout), kb = (int)((t >> 3) / cout);
@@ -445,7 +448,7 @@ int32_t gather_gemm_tc(const void *xs, int32_t cin, const float *w, int32_t K, i
     uint8_t *wsplit = reinterpret_cast<uint8_t *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     const int Kf = K * cin, n_kb = (int)div_up(Kf, BKE), bn = bn_for(cout);
     const long long chunks = (long long)n_kb * cout * 8;
-    weight_split_kernel<<<(unsigned)div_up(chunks, 256), 256, 0, stream>>>(w, cout, Kf, n_kb, bn, wsplit);
+    weight_split_kernel<<<(unsigned)div_up(chunks, 256), 256, 0, stream>>>(w, cout, Kf, n_kb, bn, wsplit, stats);
     count_launch();
     TcArgs a{bias, scale, shift, residual, reinterpret_cast<const uint8_t *>(xs), wsplit, nbr, stats, y, m_out, cin, K, cout, relu};
     switch (cout) {

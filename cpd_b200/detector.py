@@ -30,6 +30,7 @@ class CPDHotPathDetector(nn.Module):
                  max_voxels=1000000, class_names=("Vehicle", "Pedestrian", "Cyclist"), res_backbone=True,
                  predict_boxes_when_training=True):
         super().__init__()
+        self._side = None
         cfg = model_cfg or MODEL_CFG
         self.pc_range = [float(v) for v in pc_range]
         self.voxel_size = [float(v) for v in voxel_size]
@@ -49,18 +50,67 @@ class CPDHotPathDetector(nn.Module):
         frames = [f if f.is_cuda else f.to(device, non_blocking=True) for f in frames]
         return voxel.voxelize_batch(frames, self.pc_range, self.voxel_size, self.max_pts, self.max_voxels)
 
-    def forward(self, batch):
-        """batch: dict(points=[...], points1=[...] (training, MM tower), gt_boxes=(B, M, 8) (training)).
-        Training returns (loss, tb_dict); eval returns per-frame prediction dicts."""
-        device = next(self.parameters()).device
+    def _input_stage(self, batch, device, plan):
+        """The input side of a step: H2D of the raw sweeps, voxelize (+MeanVFE) both clouds, and -- with plan=True --
+        the towers' visiting order and rulebook chains (everything with a data-dependent size)."""
         bd = self._voxelize(batch["points"], device)
-        bd["batch_size"] = len(batch["points"])
-        if self.training and "points1" in batch and getattr(self.backbone_3d, "RES", False):
+        bd["batch_size"] = bs = len(batch["points"])
+        mm = self.training and "points1" in batch and getattr(self.backbone_3d, "RES", False)
+        if mm:
             b1 = self._voxelize(batch["points1"], device)
             bd["voxel_features1"], bd["voxel_coords1"] = b1["voxel_features"], b1["voxel_coords"]
         if "gt_boxes" in batch:
             gt = batch["gt_boxes"]
             bd["gt_boxes"] = gt if gt.is_cuda else gt.to(device, non_blocking=True)
+        if plan:
+            bd["tower_plan"] = self.backbone_3d.plan_tower("", bd["voxel_coords"], bs, True)
+            if mm:
+                bd["tower_plan1"] = self.backbone_3d.plan_tower("_2", bd["voxel_coords1"], bs, False)
+        return bd
+
+    def prepare(self, batch):
+        """Run the input stage of a step on a side stream (the device-side analogue of a prefetching DataLoader):
+        called right after the previous step's backward has been enqueued, its kernels and its host syncs overlap
+        that backward instead of draining the device at the start of the next forward.  Inputs must already be
+        valid (host tensors, or device tensors whose producers have finished).  Pass the result to forward()."""
+        device = next(self.parameters()).device
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=device)
+        with torch.cuda.stream(self._side):
+            bd = self._input_stage(batch, device, plan=True)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        bd["_ready"] = ev
+        return bd
+
+    @staticmethod
+    def _adopt(obj, stream, seen):
+        """Tensors made on the side stream are consumed on `stream`: tell the caching allocator."""
+        if isinstance(obj, torch.Tensor):
+            if obj.is_cuda and id(obj) not in seen:
+                seen.add(id(obj))
+                obj.record_stream(stream)
+        elif isinstance(obj, dict):
+            for v in obj.values():
+                CPDHotPathDetector._adopt(v, stream, seen)
+        elif isinstance(obj, (list, tuple)):
+            for v in obj:
+                CPDHotPathDetector._adopt(v, stream, seen)
+        elif hasattr(obj, "__dict__") and not isinstance(obj, (torch.cuda.Event, nn.Module)):
+            CPDHotPathDetector._adopt(vars(obj), stream, seen)
+
+    def forward(self, batch, prepared=None):
+        """batch: dict(points=[...], points1=[...] (training, MM tower), gt_boxes=(B, M, 8) (training)).
+        prepared: the result of prepare(batch) (optional).  Training returns (loss, tb_dict); eval returns
+        per-frame prediction dicts."""
+        device = next(self.parameters()).device
+        if prepared is not None:
+            bd = prepared
+            main = torch.cuda.current_stream(device)
+            main.wait_event(bd.pop("_ready"))
+            self._adopt(bd, main, set())
+        else:
+            bd = self._input_stage(batch, device, plan=False)
         bd = self.vfe(bd)
         bd = self.backbone_3d(bd)
         bd = self.map_to_bev_module(bd)

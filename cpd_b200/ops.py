@@ -172,6 +172,16 @@ ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05 = 0, 1, 2
 PROFILE = None
 
 
+def tc_gemm_ok(cin, K, cout):
+    """Shapes the tcgen05 gather-GEMM takes under ALGO_AUTO (mirrors cpd_gather_gemm's dispatch)."""
+    return cin % 8 == 0 and cin >= 8 and K <= 27 and (cout in (16, 32, 64, 128) or (cout % 256 == 0 and 0 < cout <= 2048))
+
+
+def tc_wgrad_ok(cin, K, cout):
+    """Shapes the row-stationary tcgen05 weight-gradient takes (mirrors gather_wgrad_rows_supported)."""
+    return cin >= 8 and cin % 8 == 0 and ((cin <= 256 and 256 % cin == 0) or cin % 256 == 0) and cout >= 8 and cout % 8 == 0 and K <= 64
+
+
 def split_rows(x):
     """Split-row image of a row matrix (m, c), c % 8 == 0: (m, 2, c) bf16, row = [hi(c) | lo(c)] -- the operand
     format of the tcgen05 kernels (include/cpd_b200.h).  Returns None when the layout does not apply."""

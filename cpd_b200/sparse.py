@@ -112,8 +112,23 @@ class _GatherConv(torch.autograd.Function):
         ctx.rb, ctx.algo = rb, algo
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        stats = torch.zeros((2, weight.shape[0]), dtype=torch.float32, device=x.device) if want_stats else None
-        y = ops.gather_gemm(x, weight, rb.nbr_fwd, bias=bias, stats=stats, algo=algo)
+        stats = torch.empty((2, weight.shape[0]), dtype=torch.float32, device=x.device) if want_stats else None   # cleared by the call
+        cout, cin, K = weight.shape[0], weight.shape[-1], rb.nbr_fwd.shape[1]
+        # narrow outputs (the 1-3 channel CenterHead maps): zero-pad the output channels so the tensor-core kernels apply
+        ctx.pad_out = algo != ops.ALGO_SIMT and cout < 8 and cin % 8 == 0 and not want_stats
+        if ctx.pad_out:
+            wp = torch.nn.functional.pad(weight.reshape(cout, K, cin), (0, 0, 0, 0, 0, 16 - cout))
+            bp = torch.nn.functional.pad(bias, (0, 16 - cout)) if bias is not None else None
+            ctx.xs = None
+            return ops.gather_gemm(x, wp, rb.nbr_fwd, bias=bp, algo=algo)[:, :cout].contiguous()
+        # the split-row image of x (bf16 hi | lo, the tcgen05 operand format) is built once and shared by the
+        # forward GEMM and the weight-gradient
+        needs_grad = weight.requires_grad and torch.is_grad_enabled()
+        xs = None
+        if algo != ops.ALGO_SIMT and (ops.tc_gemm_ok(cin, K, cout) or (needs_grad and ops.tc_wgrad_ok(cin, K, cout))):
+            xs = ops.split_rows(x)
+        ctx.xs = xs if needs_grad else None
+        y = ops.gather_gemm(x, weight, rb.nbr_fwd, bias=bias, stats=stats, algo=algo, x_split=xs)
         if not want_stats:
             return y
         ctx.mark_non_differentiable(stats)
@@ -125,19 +140,38 @@ class _GatherConv(torch.autograd.Function):
         rb = ctx.rb
         dy = dy.contiguous()
         dx = dw = db = None
+        cout, cin, K = weight.shape[0], weight.shape[-1], rb.nbr_fwd.shape[1]
+        want_w = ctx.needs_input_grad[1] or ctx.has_bias
+        if ctx.pad_out:                                # dy (m, cout < 8) -> (m, 8): zero channels contribute nothing
+            dyp = torch.nn.functional.pad(dy, (0, 8 - cout))
+            dys = ops.split_rows(dyp)
+            if ctx.needs_input_grad[0]:
+                wt = torch.nn.functional.pad(ops.weight_transpose(weight, flip_taps=rb.kind == "subm"), (0, 8 - cout))
+                dx = ops.gather_gemm(dyp, wt, rb.nbr_fwd if rb.kind == "subm" else rb.nbr_bwd, algo=ctx.algo, x_split=dys)
+            if want_w:
+                tm = K > 1
+                dwp, dbp = ops.gather_wgrad(x, dyp, rb.nbr_fwd_t if tm else rb.nbr_fwd, want_bias=ctx.has_bias, tap_major=tm, dy_split=dys)
+                dw, db = dwp[:cout].reshape(weight.shape), (dbp[:cout] if dbp is not None else None)
+            return dx, dw, db, None, None, None
+        # one split-row image of dy serves the input-gradient GEMM and the weight-gradient
+        dys = None
+        if ctx.algo != ops.ALGO_SIMT and ((ctx.needs_input_grad[0] and ops.tc_gemm_ok(cout, K, cin)) or
+                                          (want_w and ops.tc_wgrad_ok(cin, K, cout))):
+            dys = ops.split_rows(dy)
         if ctx.needs_input_grad[0]:
             if rb.kind == "subm":
                 wt = ops.weight_transpose(weight, flip_taps=True)
-                dx = ops.gather_gemm(dy, wt, rb.nbr_fwd, algo=ctx.algo)
+                dx = ops.gather_gemm(dy, wt, rb.nbr_fwd, algo=ctx.algo, x_split=dys)
             else:
                 wt = ops.weight_transpose(weight, flip_taps=False)
-                dx = ops.gather_gemm(dy, wt, rb.nbr_bwd, algo=ctx.algo)
-        if ctx.needs_input_grad[1] or ctx.has_bias:
+                dx = ops.gather_gemm(dy, wt, rb.nbr_bwd, algo=ctx.algo, x_split=dys)
+        if want_w:
             if rb.nbr_fwd.shape[1] > 1:
-                dw, db = ops.gather_wgrad(x, dy, rb.nbr_fwd_t, want_bias=ctx.has_bias, tap_major=True)
+                dw, db = ops.gather_wgrad(x, dy, rb.nbr_fwd_t, want_bias=ctx.has_bias, tap_major=True, x_split=ctx.xs, dy_split=dys)
             else:
-                dw, db = ops.gather_wgrad(x, dy, rb.nbr_fwd, want_bias=ctx.has_bias)
+                dw, db = ops.gather_wgrad(x, dy, rb.nbr_fwd, want_bias=ctx.has_bias, x_split=ctx.xs, dy_split=dys)
             dw = dw.view_as(weight)
+        ctx.xs = None
         return dx, dw, db, None, None, None
 
 

@@ -123,7 +123,7 @@ CPD_API int32_t cpd_rulebook_strided_tables(const int32_t *in_coords, int64_t m_
  * epilogue: + bias[cout] (NULL ok); * scale[cout] + shift[cout] (NULL ok: folded
  * eval-mode BatchNorm, spconv_backbone.py:410); + residual[o,:] (NULL ok:
  * SparseBasicBlock, spconv_backbone.py:100-136); ReLU if relu != 0.
- * stats (NULL ok): (2, cout) fp32 accumulators receiving per-channel sum and sum of
+ * stats (NULL ok): (2, cout) fp32, overwritten with the per-channel sum and sum of
  * squares of the pre-affine output (training-mode BatchNorm statistics).
  * --------------------------------------------------------------------------------- */
 enum cpd_gemm_algo { CPD_ALGO_AUTO = 0, CPD_ALGO_SIMT = 1, CPD_ALGO_TCGEN05 = 2 };
