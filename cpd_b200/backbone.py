@@ -151,6 +151,9 @@ class _Backbone8xBase(nn.Module):
                     rb, out_hash = m.get_rulebook(x)
                     if rb.nbr_fwd.shape[1] > 1:
                         rb.nbr_fwd_t                  # transposed table for the weight-gradient kernel
+                    rb.masks_fwd                      # per-tile tap masks (k-block skipping)
+                    if rb.kind == "strided" and self.training:
+                        rb.bwd_sorted()               # input-gradient table grouped by tap pattern
                     x = m._wrap_output(x, rb, out_hash, None)
         return dict(perm=perm, coords=coords, indice_dict=x.indice_dict)
 

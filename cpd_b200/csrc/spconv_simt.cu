@@ -10,9 +10,10 @@
 
 namespace cpd {
 
-int32_t split_rows(const float *x, int64_t m, int32_t c, void *xs, cudaStream_t stream);
+int32_t split_rows(const float *x, int64_t m, int32_t c, void *xs, float *colsum, cudaStream_t stream);
+int32_t tile_tap_masks(const int32_t *nbr, int64_t m, int32_t K, uint32_t *masks, cudaStream_t stream);
 int32_t gather_gemm_tc(const void *xs, int32_t cin, const float *w, int32_t K, int32_t cout,
-                       const int32_t *nbr, int64_t m_out, const float *bias, const float *scale, const float *shift,
+                       const int32_t *nbr, const uint32_t *tile_masks, int64_t m_out, const float *bias, const float *scale, const float *shift,
                        const float *residual, int32_t relu, float *stats, float *y, void *ws, size_t ws_bytes,
                        cudaStream_t stream);
 size_t gather_gemm_tc_workspace(int32_t cin, int32_t K, int32_t cout);
@@ -339,8 +340,14 @@ extern "C" size_t cpd_gather_gemm_workspace_bytes(int64_t m_in, int64_t, int32_t
     return 256 + gather_gemm_tc_workspace(cin, K, cout) + (have_x_split ? 0 : image_bytes(m_in, cin));
 }
 
+extern "C" int32_t cpd_tile_tap_masks(const int32_t *nbr, int64_t m, int32_t K, uint32_t *masks, cpd_stream_t stream)
+{
+    CPD_REQUIRE(nbr && masks && m >= 0, CPD_ERR_BAD_ARG, "cpd_tile_tap_masks: bad argument");
+    return tile_tap_masks(nbr, m, K, masks, (cudaStream_t)stream);
+}
+
 extern "C" int32_t cpd_gather_gemm(const float *x, const void *x_split, int64_t m_in, int32_t cin, const float *w, int32_t K,
-                                   int32_t cout, const int32_t *nbr, int64_t m_out, const float *bias, const float *scale,
+                                   int32_t cout, const int32_t *nbr, const uint32_t *tile_masks, int64_t m_out, const float *bias, const float *scale,
                                    const float *shift, const float *residual, int32_t relu, float *stats, float *y,
                                    int32_t algo, void *ws, size_t ws_bytes, cpd_stream_t stream_)
 {
@@ -364,13 +371,13 @@ extern "C" int32_t cpd_gather_gemm(const float *x, const void *x_split, int64_t 
         uint8_t *p = reinterpret_cast<uint8_t *>(align_up((size_t)(uintptr_t)ws, 256));
         const void *xs = x_split;
         if (!xs) {                                   // build the split-row image of x in the workspace
-            int32_t st = split_rows(x, m_in, cin, p, stream);
+            int32_t st = split_rows(x, m_in, cin, p, nullptr, stream);
             if (st) return st;
             xs = p;
             p += image_bytes(m_in, cin);
         }
         const size_t left = ws_bytes - (size_t)(p - reinterpret_cast<uint8_t *>(ws));
-        return gather_gemm_tc(xs, cin, w, K, cout, nbr, m_out, bias, scale, shift, residual, relu, stats, y, p, left, stream);
+        return gather_gemm_tc(xs, cin, w, K, cout, nbr, tile_masks, m_out, bias, scale, shift, residual, relu, stats, y, p, left, stream);
     }
     CPD_REQUIRE(x, CPD_ERR_BAD_ARG, "cpd_gather_gemm: the SIMT kernel needs the fp32 rows");
     if (stats) CPD_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)cout, stream));
@@ -417,13 +424,13 @@ extern "C" int32_t cpd_gather_wgrad(const float *x, const void *x_split, int64_t
             uint8_t *p = reinterpret_cast<uint8_t *>(align_up((size_t)(uintptr_t)ws, 256));
             const void *xs = x_split, *dys = dy_split;
             if (!xs) {
-                st = split_rows(x, m_in, cin, p, stream);
+                st = split_rows(x, m_in, cin, p, nullptr, stream);
                 if (st) return st;
                 xs = p;
                 p += image_bytes(m_in, cin);
             }
             if (!dys) {
-                st = split_rows(dy, m_out, cout, p, stream);
+                st = split_rows(dy, m_out, cout, p, nullptr, stream);
                 if (st) return st;
                 dys = p;
             }

@@ -11,9 +11,11 @@
 // k-block, a 128-channel layer spends two k-blocks per tap.  W (cout, K, cin) is already contiguous
 // along f, so the B operand of k-block kb is simply W[:, 64 kb : 64 kb + 64].
 //
-// PERSISTENT, warp-specialised: one CTA per SM walks the (128-row x BN-channel) output tiles
-// blockIdx.x, blockIdx.x + gridDim.x, ...; the operand pipeline never drains between tiles and the
-// epilogue of tile i overlaps the main loop of tile i+1 (double-buffered TMEM accumulators).
+// PERSISTENT, warp-specialised: one CTA per SM pulls (128-row x BN-channel) output tiles from a global
+// atomic counter (dynamic scheduling: a CTA that starts late or shares its SM with another stream's
+// kernels -- NCCL under DDP, the prefetched input stage -- simply takes fewer tiles); the operand
+// pipeline never drains between tiles and the epilogue of tile i overlaps the main loop of tile i+1
+// (double-buffered TMEM accumulators).
 //   weight_split_kernel (one tiny launch before the GEMM): W -> bf16 hi / lo images stored in
 //              global memory ALREADY in the swizzled shared-memory tile layout, one contiguous
 //              [hi | lo] block of 2 * BN * 128 bytes per (k-block, cout tile).
@@ -61,6 +63,9 @@ constexpr int NTHREADS = NEPI + NPROD + 64;
 constexpr int RSTEP = NPROD / 8;   // row stride between the chunks one producer thread owns (8 x 16 B chunks per row)
 constexpr int A_V = BM / RSTEP;    // rows per producer thread per k-block
 constexpr int MAX_TAPS = 27;
+constexpr int SCHED_R = 4;                     // depth of the tile-id ring
+constexpr int KBW = 4;                         // 32-bit words of the per-tile active-k-block bitmap (n_kb <= 128)
+constexpr int NCONS = NTHREADS / 32;           // every warp consumes the tile sequence
 
 __host__ __device__ constexpr int stage_bytes(int bn) { return 2 * BM * 128 + 2 * bn * 128; }
 __host__ __device__ constexpr int stages_for(int bn) { return bn >= 256 ? 2 : bn >= 128 ? 3 : bn >= 32 ? 4 : 5; }
@@ -87,6 +92,8 @@ struct TcArgs {
     const uint8_t *xs;          // split-row image of x: row i = [hi(cin) | lo(cin)] bf16 (split.cu)
     const uint8_t *wsplit;      // [k-block][cout tile][hi | lo][BN rows x 128 B, swizzled]
     const int32_t *nbr;         // (m_out, K)
+    unsigned int *tile_counter; // dynamic tile scheduler (zeroed by weight_split_kernel)
+    const uint32_t *tile_masks; // NULL ok: per 128-row tile, bit k = tap k has a neighbour in the tile (cpd_tile_tap_masks)
     float *stats, *y;
     long long m_out;
     int cin, K, cout, relu;
@@ -95,10 +102,11 @@ struct TcArgs {
 // W (cout, Kf) fp32 -> pre-swizzled bf16 hi / lo tile images.  One thread per 16-byte output chunk.
 // Also clears the (2, cout) BatchNorm statistics accumulators of the GEMM that follows on the stream.
 __global__ void weight_split_kernel(const float *__restrict__ w, int cout, int Kf, int n_kb, int bn, uint8_t *__restrict__ out,
-                                    float *__restrict__ stats)
+                                    float *__restrict__ stats, unsigned int *__restrict__ tile_counter)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (stats && t < 2 * cout) stats[t] = 0.f;
+    if (t == 0) *tile_counter = 0u;
     if (t >= (long long)n_kb * cout * 8) return;
     const int c = (int)(t & 7);
     const int n = (int)((t >> 3) % cout), kb = (int)((t >> 3) / cout);
@@ -146,9 +154,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
     const int tbl_ints = BM * a.K;
     int32_t *nbr_s = reinterpret_cast<int32_t *>(tiles + STAGES * STAGE);          // [2][BM][K]
     uint64_t *bars = reinterpret_cast<uint64_t *>(nbr_s + 2 * tbl_ints);          // full[S] empty[S] tbl_full[2] tbl_empty[2] acc_full[2] acc_empty[2]
-    uint32_t *misc = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 8);         // [0] tmem base
+    uint32_t *misc = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 8 + 2 * SCHED_R);   // [0] tmem base, [4..) tile ring
+    volatile int32_t *sched_tile = reinterpret_cast<volatile int32_t *>(misc + 4);       // [R] tile id
+    volatile uint32_t *sched_kb = reinterpret_cast<volatile uint32_t *>(misc + 4 + SCHED_R);   // [R][KBW] active k-blocks of the tile
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * STAGES, tblf0 = empty0 + 8 * STAGES, tble0 = tblf0 + 16,
-                   accf0 = tble0 + 16, acce0 = accf0 + 16;
+                   accf0 = tble0 + 16, acce0 = accf0 + 16, schf0 = acce0 + 16, sche0 = schf0 + 8 * SCHED_R;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Kf = a.K * a.cin;
@@ -163,6 +173,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
                 mbar_init(tblf0 + 8 * b, 1); mbar_init(tble0 + 8 * b, NPW);
                 mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, NEPI / 32);
             }
+            for (int r = 0; r < SCHED_R; ++r) { mbar_init(schf0 + 8 * r, 1); mbar_init(sche0 + 8 * r, NCONS); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -173,6 +184,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = misc[0];
+    // Every warp walks the same tile sequence: entry ti of the ring is published by the loader warp (atomicAdd on the
+    // global counter) and released once all NCONS warps have read it.  A value >= total_tiles ends the sequence.
+    // The entry also carries the bitmap of the tile's ACTIVE k-blocks (those with at least one tap that has a neighbour
+    // somewhere in the tile, from tile_masks): every role skips the others -- z-boundary tiles of a SubM conv lose a third
+    // of their taps, a parity-sorted strided input-gradient keeps <= 8 of 27.
+    uint32_t km0 = 0, km1 = 0, km2 = 0, km3 = 0;   // scalars, not an array: must stay in registers
+    static_assert(KBW == 4, "bitmap words are spelled out");
+    auto fetch_tile = [&](int ti) -> long long {
+        const int slot = ti % SCHED_R;
+        mbar_wait(schf0 + 8 * slot, (ti / SCHED_R) & 1);
+        const long long t = sched_tile[slot];
+        km0 = sched_kb[slot * KBW]; km1 = sched_kb[slot * KBW + 1]; km2 = sched_kb[slot * KBW + 2]; km3 = sched_kb[slot * KBW + 3];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sche0 + 8 * slot);
+        return t;
+    };
+    auto kb_bit = [](int kb, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) -> bool {
+        const int w = kb >> 5;
+        const uint32_t word = w == 0 ? w0 : w == 1 ? w1 : w == 2 ? w2 : w3;
+        return (word >> (kb & 31)) & 1u;
+    };
+    auto kb_active = [&](int kb) -> bool { return kb_bit(kb, km0, km1, km2, km3); };
 
     if (warp < NEPI / 32) {
         // ================= epilogue (warps 0-3; TMEM lanes 32 * warp .. + 31 = tile rows) =================
@@ -180,7 +213,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
 #pragma unroll
         for (int i = 0; i < BN / 16; ++i) st_acc[i] = 0.f;
         int ti = 0;
-        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+        for (long long t = fetch_tile(0); t < total_tiles; t = fetch_tile(++ti)) {
             const int buf = ACC == 2 ? (ti & 1) : 0;
             mbar_wait(accf0 + 8 * buf, ACC == 2 ? ((ti >> 1) & 1) : (ti & 1));
             tc_fence_after();
@@ -256,13 +289,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
         const size_t row_bytes = (size_t)a.cin * 4;                // image row = hi(cin) | lo(cin) bf16
         const uint32_t lo_off = (uint32_t)a.cin * 2;
         int g = 0, ti = 0;                            // k-blocks issued so far (all tiles), tiles started
-        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+        for (long long t = fetch_tile(0); t < total_tiles; t = fetch_tile(++ti)) {
             const long long row0 = (t / ntn) * BM;
             const int tb = ti & 1;
             mbar_wait(tblf0 + 8 * tb, (ti >> 1) & 1);                              // this tile's slice of the neighbour table has landed
             const int32_t *tab = nbr_s + tb * tbl_ints + r_base * a.K;
             int rows_left = (int)min((long long)BM, a.m_out - row0) - r_base;     // rows r_base + RSTEP j < rows of the tile
-            for (int kb = 0; kb < n_kb; ++kb, ++g) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+                if (!kb_active(kb)) continue;
                 const int s = g % STAGES;
                 mbar_wait(empty0 + 8 * s, ((g / STAGES) & 1) ^ 1);
                 const int f = kb * BKE + c * 8;        // flattened (tap, channel) index of this thread's chunk
@@ -279,6 +313,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
                     cp_async16(dst + A_BYTES + soff[j], src + lo_off, sz);
                 }
                 cp_async_arrive_noinc(full0 + 8 * s);    // this thread's arrival fires when its copies above have landed
+                ++g;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(tble0 + 8 * tb);                            // table copy no longer needed by this warp
@@ -297,12 +332,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
         const uint32_t tiles_u32 = smem_u32(tiles);
         const int last_k16 = (Kf - (n_kb - 1) * BKE + 15) / 16;       // K steps of the last (possibly partial) k-block
         int g = 0, ti = 0;
-        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+        for (long long t = fetch_tile(0); t < total_tiles; t = fetch_tile(++ti)) {
             const int buf = ACC == 2 ? (ti & 1) : 0;
             mbar_wait(acce0 + 8 * buf, (ACC == 2 ? ((ti >> 1) & 1) : (ti & 1)) ^ 1);   // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_main = tmem_base + (uint32_t)(buf * 2 * BN), d_corr = d_main + (uint32_t)BN;
-            for (int kb = 0; kb < n_kb; ++kb, ++g) {
+            bool first = true;                        // the tile's first instruction overwrites the accumulators
+            for (int kb = 0; kb < n_kb; ++kb) {
+                if (!kb_active(kb)) continue;
                 const int s = g % STAGES;
                 mbar_wait(full0 + 8 * s, (g / STAGES) & 1);
                 fence_async_smem();        // the producers' cp.async writes (generic proxy), observed through the barrier -> async proxy
@@ -316,11 +353,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
                         if (k16 < k16n) {
                             const uint64_t adv = (uint64_t)(k16 * 2);            // +32 bytes along K inside the swizzle row
                             if (BN <= 128) {
-                                if (kb == 0 && k16 == 0) umma_bf16_set(d_main, a_hi, b_hi, IDESC2);
+                                if (first && k16 == 0) umma_bf16_set(d_main, a_hi, b_hi, IDESC2);
                                 else umma_bf16_acc(d_main, a_hi + adv, b_hi + adv, IDESC2);           // [main | corr] += A_hi.[B_hi | B_lo]
                                 umma_bf16_acc(d_corr, a_lo + adv, b_hi + adv, IDESC);                // corr += A_lo.B_hi
                             } else {
-                                if (kb == 0 && k16 == 0) {
+                                if (first && k16 == 0) {
                                     umma_bf16_set(d_main, a_hi, b_hi, IDESC);
                                     umma_bf16_set(d_corr, a_lo, b_hi, IDESC);
                                 } else {
@@ -332,10 +369,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
                         }
                     }
                     umma_commit(empty0 + 8 * s);            // frees the stage once these MMAs have read it
-                    if (kb == n_kb - 1) umma_commit(accf0 + 8 * buf);
                 }
                 __syncwarp();
+                first = false;
+                ++g;
             }
+            if (elect_one()) umma_commit(accf0 + 8 * buf);  // all of the tile's MMAs done -> epilogue
+            __syncwarp();
         }
         tc_fence_before();
     } else {
@@ -358,17 +398,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
                 if (lane == 0) mbar_arrive(tblf0 + 8 * tb);
             }
         };
-        if ((long long)blockIdx.x < total_tiles) load_table(blockIdx.x, 0);
+        auto publish = [&](int j) {                          // tile-id ring entry j <- next tile from the global counter
+            const int slot = j % SCHED_R;
+            mbar_wait(sche0 + 8 * slot, ((j / SCHED_R) & 1) ^ 1);
+            unsigned int t = 0;
+            if (lane == 0) t = atomicAdd(a.tile_counter, 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            uint32_t mask = 0xffffffffu;
+            if (a.tile_masks && (long long)t < total_tiles) mask = __ldg(a.tile_masks + t / ntn);
+            bool any = false;
+            for (int w = 0; w < KBW; ++w) {               // lane l decides k-block 32 w + l
+                const int kb = 32 * w + lane;
+                bool act = false;
+                if (kb < n_kb) {
+                    const int t0 = (kb * BKE) / a.cin;
+                    int t1 = (kb * BKE + BKE - 1) / a.cin;
+                    if (t1 > a.K - 1) t1 = a.K - 1;
+                    const uint32_t upto = t1 >= 31 ? 0xffffffffu : ((1u << (t1 + 1)) - 1u);
+                    act = (mask & upto & ~((1u << t0) - 1u)) != 0u;
+                }
+                uint32_t bits = __ballot_sync(0xffffffffu, act);
+                any |= bits != 0u;
+                if (lane == 0) sched_kb[slot * KBW + w] = bits;
+            }
+            if (!any && lane == 0) sched_kb[slot * KBW] = 1u;   // an empty tile still runs k-block 0 (all zero rows -> zero output)
+            if (lane == 0) {
+                sched_tile[slot] = (int32_t)(t < 0x7fffffffu ? t : 0x7fffffffu);
+                mbar_arrive(schf0 + 8 * slot);
+            }
+            __syncwarp();
+        };
+        publish(0);
+        long long t = fetch_tile(0);
+        if (t < total_tiles) load_table(t, 0);
         int g = 0, ti = 0;
-        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
-            const long long t_next = t + gridDim.x;
+        for (; t < total_tiles; ++ti) {
+            const uint32_t c0 = km0, c1 = km1, c2 = km2, c3 = km3;     // this tile's k-block map (fetch_tile overwrites km*)
+            auto kb_active_cur = [&](int kb) -> bool { return kb_bit(kb, c0, c1, c2, c3); };
+            publish(ti + 1);
+            const long long t_next = fetch_tile(ti + 1);
             if (t_next < total_tiles) {
                 const int tbn = (ti + 1) & 1;
                 mbar_wait(tble0 + 8 * tbn, (((ti + 1) >> 1) & 1) ^ 1);             // producers are done with the tile that used this buffer
                 load_table(t_next, tbn);
             }
             const int nt = (int)(t % ntn);
-            for (int kb = 0; kb < n_kb; ++kb, ++g) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+                if (!kb_active_cur(kb)) continue;
                 const int s = g % STAGES;
                 if (lane == 0) {
                     mbar_wait(empty0 + 8 * s, ((g / STAGES) & 1) ^ 1);
@@ -377,7 +453,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
                     bulk_copy_g2s(smem_u32(tiles + s * STAGE + 2 * A_BYTES), src, tile_bytes, full0 + 8 * s);
                 }
                 __syncwarp();
+                ++g;
             }
+            t = t_next;
         }
     }
     __syncthreads();
@@ -390,7 +468,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
 template <int BN>
 size_t smem_bytes(int K)
 {
-    return 1024 + (size_t)stages_for(BN) * stage_bytes(BN) + (size_t)2 * K * BM * 4 + (2 * stages_for(BN) + 8) * 8 + 16;
+    return 1024 + (size_t)stages_for(BN) * stage_bytes(BN) + (size_t)2 * K * BM * 4 + (2 * stages_for(BN) + 8 + 2 * SCHED_R) * 8 + 16 +
+           SCHED_R * 4 * (1 + KBW);
 }
 
 int num_sms()
@@ -426,7 +505,7 @@ inline int bn_for(int cout) { return cout >= 256 ? 256 : cout; }
 
 bool gather_gemm_tc_supported(int32_t cin, int32_t K, int32_t cout)
 {
-    return cin % 8 == 0 && cin >= 8 && K <= MAX_TAPS &&
+    return cin % 8 == 0 && cin >= 8 && K <= MAX_TAPS && (long long)K * cin <= 32ll * KBW * BKE &&
            (cout == 16 || cout == 32 || cout == 64 || cout == 128 || (cout >= 256 && cout % 256 == 0 && cout <= 2048));
 }
 
@@ -434,23 +513,50 @@ bool gather_gemm_tc_supported(int32_t cin, int32_t K, int32_t cout)
 size_t gather_gemm_tc_workspace(int32_t cin, int32_t K, int32_t cout)
 {
     const size_t n_kb = (size_t)div_up((long long)K * cin, BKE);
-    return 256 + n_kb * (size_t)cout * 256;
+    return 512 + n_kb * (size_t)cout * 256;              // tile counter + weight image
+}
+
+// One bit per tap and 128-row tile: does any row of the tile have a neighbour at that tap?
+__global__ void tile_masks_kernel(const int32_t *__restrict__ nbr, long long m, int K, uint32_t *__restrict__ masks)
+{
+    __shared__ uint32_t acc;
+    if (threadIdx.x == 0) acc = 0u;
+    __syncthreads();
+    const long long row = (long long)blockIdx.x * 128 + threadIdx.x;
+    uint32_t mine = 0u;
+    if (row < m)
+        for (int k = 0; k < K; ++k)
+            if (__ldg(nbr + row * K + k) >= 0) mine |= 1u << k;
+    mine = __reduce_or_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicOr(&acc, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) masks[blockIdx.x] = acc;
+}
+
+int32_t tile_tap_masks(const int32_t *nbr, int64_t m, int32_t K, uint32_t *masks, cudaStream_t stream)
+{
+    CPD_REQUIRE(K >= 1 && K <= 32, CPD_ERR_UNSUPPORTED, "cpd_tile_tap_masks: at most 32 taps");
+    if (m == 0) return CPD_OK;
+    tile_masks_kernel<<<(unsigned)div_up(m, 128), 128, 0, stream>>>(nbr, m, K, masks);
+    count_launch();
+    return launch_status("cpd_tile_tap_masks");
 }
 
 int32_t gather_gemm_tc(const void *xs, int32_t cin, const float *w, int32_t K, int32_t cout, const int32_t *nbr,
-                       int64_t m_out, const float *bias, const float *scale, const float *shift, const float *residual,
+                       const uint32_t *tile_masks, int64_t m_out, const float *bias, const float *scale, const float *shift, const float *residual,
                        int32_t relu, float *stats, float *y, void *ws, size_t ws_bytes, cudaStream_t stream)
 {
     CPD_REQUIRE(gather_gemm_tc_supported(cin, K, cout), CPD_ERR_UNSUPPORTED, "tcgen05 gather-GEMM: unsupported shape");
     CPD_REQUIRE((((uintptr_t)xs | (uintptr_t)w | (uintptr_t)y | (uintptr_t)bias | (uintptr_t)scale | (uintptr_t)shift |
                   (uintptr_t)residual | (uintptr_t)nbr) & 15) == 0, CPD_ERR_MISALIGNED, "tcgen05 gather-GEMM: pointers must be 16-byte aligned");
     CPD_REQUIRE(ws && ws_bytes >= gather_gemm_tc_workspace(cin, K, cout), CPD_ERR_WORKSPACE, "tcgen05 gather-GEMM: workspace too small");
-    uint8_t *wsplit = reinterpret_cast<uint8_t *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    unsigned int *tile_counter = reinterpret_cast<unsigned int *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    uint8_t *wsplit = reinterpret_cast<uint8_t *>(tile_counter) + 256;
     const int Kf = K * cin, n_kb = (int)div_up(Kf, BKE), bn = bn_for(cout);
     const long long chunks = (long long)n_kb * cout * 8;
-    weight_split_kernel<<<(unsigned)div_up(chunks, 256), 256, 0, stream>>>(w, cout, Kf, n_kb, bn, wsplit, stats);
+    weight_split_kernel<<<(unsigned)div_up(chunks, 256), 256, 0, stream>>>(w, cout, Kf, n_kb, bn, wsplit, stats, tile_counter);
     count_launch();
-    TcArgs a{bias, scale, shift, residual, reinterpret_cast<const uint8_t *>(xs), wsplit, nbr, stats, y, m_out, cin, K, cout, relu};
+    TcArgs a{bias, scale, shift, residual, reinterpret_cast<const uint8_t *>(xs), wsplit, nbr, tile_counter, tile_masks, stats, y, m_out, cin, K, cout, relu};
     switch (cout) {
         case 16: return launch_tc<16>(a, stream);
         case 32: return launch_tc<32>(a, stream);

@@ -26,6 +26,7 @@
 // For cout tiles narrower than 128 only one 64-column block of the A tile exists in shared memory: the
 // descriptor's second block aliases whatever follows, which only pollutes accumulator
 // lanes >= AM that are never read.
+#include <algorithm>
 #include "tc_common.cuh"
 
 namespace cpd {
@@ -38,7 +39,7 @@ constexpr int NPW = 8;            // producer / epilogue warps
 constexpr int NPROD = NPW * 32;
 constexpr int NTHREADS = NPROD + 32;
 constexpr int MAX_T = 32;        // taps per group (cin = 8 -> 32 taps in N = 256)
-constexpr int MAX_ROWS_PER_CTA = 4096;   // = 256 K-steps accumulated in one TMEM accumulator (bounds the truncation bias)
+constexpr int MAX_ROWS_PER_CTA = 8192;   // = 512 K-steps accumulated in one TMEM accumulator (bounds the truncation bias)
 
 __host__ __device__ constexpr int w_a_bytes(int am) { return KB * (am < 64 ? 64 : am) * 2; }   // whole 64-column blocks
 __host__ __device__ constexpr int w_stage_bytes(int bn, int am) { return 2 * w_a_bytes(am) + 2 * KB * bn * 2; }
@@ -244,6 +245,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
         tc_fence_before();
     } else {
         // ================= MMA issuer =================
+        constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                    ((uint32_t)((BN <= 128 ? 2 * BN : BN) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t tiles_u32 = smem_u32(tiles);
         int it = 0;
         for (; it < n_blocks; ++it) {
             const int s = it % STAGES;
@@ -252,23 +256,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
             const uint32_t k16n = (uint32_t)((nvalid + 15) / 16);
             fence_async_smem();        // producers' cp.async / zero-fill writes (generic proxy), observed through the barrier -> async proxy
             tc_fence_after();
-            if (lane == 0) {
-                const uint32_t st = smem_u32(tiles + s * STAGE);
-                const uint64_t a_hi = make_desc_mn(st), a_lo = make_desc_mn(st + A_BYTES);
-                const uint64_t b_hi = make_desc_mn(st + 2 * A_BYTES), b_lo = make_desc_mn(st + 2 * A_BYTES + B_BYTES);
+            // one elected lane, descriptors = constant + stage offset, K loop unrolled: the issue rate of the UMMA
+            // stream matters (tools/micro/mma_bench2.cu).  For BN = 128 the B tile [B_hi | B_lo] (adjacent 64-column
+            // blocks) is ONE N = 256 operand: A_hi.[B_hi|B_lo] lands in [main | corr], A_lo.B_hi is added into corr.
+            if (elect_one()) {
+                const uint64_t a_hi = make_desc_mn(tiles_u32 + (uint32_t)(s * STAGE)), a_lo = a_hi + (A_BYTES >> 4);
+                const uint64_t b_hi = a_hi + (2 * A_BYTES >> 4), b_lo = b_hi + (B_BYTES >> 4);
                 const uint32_t d_main = tmem_base, d_corr = tmem_base + (uint32_t)BN;
-                for (uint32_t k16 = 0; k16 < k16n; ++k16) {
-                    const uint64_t adv = (uint64_t)((k16 * 2048) >> 4);     // next 16-row K step (two 8-row atoms)
-                    umma_bf16(d_main, a_hi + adv, b_hi + adv, IDESC, (it | (int)k16) ? 1u : 0u);
-                    umma_bf16(d_corr, a_lo + adv, b_hi + adv, IDESC, (it | (int)k16) ? 1u : 0u);
-                    umma_bf16(d_corr, a_hi + adv, b_lo + adv, IDESC, 1u);
+#pragma unroll
+                for (int k16 = 0; k16 < KB / 16; ++k16) {
+                    if (k16 < (int)k16n) {
+                        const uint64_t adv = (uint64_t)((k16 * 2048) >> 4);     // next 16-row K step (two 8-row atoms)
+                        if (BN <= 128) {
+                            if (it == 0 && k16 == 0) umma_bf16_set(d_main, a_hi, b_hi, IDESC2);
+                            else umma_bf16_acc(d_main, a_hi + adv, b_hi + adv, IDESC2);
+                            umma_bf16_acc(d_corr, a_lo + adv, b_hi + adv, IDESC);
+                        } else {
+                            if (it == 0 && k16 == 0) {
+                                umma_bf16_set(d_main, a_hi, b_hi, IDESC);
+                                umma_bf16_set(d_corr, a_lo, b_hi, IDESC);
+                            } else {
+                                umma_bf16_acc(d_main, a_hi + adv, b_hi + adv, IDESC);
+                                umma_bf16_acc(d_corr, a_lo + adv, b_hi + adv, IDESC);
+                            }
+                            umma_bf16_acc(d_corr, a_hi + adv, b_lo + adv, IDESC);
+                        }
+                    }
                 }
                 umma_commit(empty0 + 8 * s);
+                if (it == n_blocks - 1) umma_commit(accum_bar);
             }
             __syncwarp();
         }
-        if (it > 0 && lane == 0) umma_commit(accum_bar);
-        __syncwarp();
         tc_fence_before();
     }
     __syncthreads();
@@ -330,13 +349,17 @@ int32_t gather_wgrad_rows_tc(const void *xs, int32_t cin, const void *dys, int64
     if (tpg > MAX_T) tpg = MAX_T;
     if (tpg > K) tpg = K;
     const int groups = (int)div_up(K, tpg), co_tiles = (int)div_up(cout, 128);
-    // row slices: enough CTAs for ~2 per SM, but at most MAX_STEPS_PER_CTA k8 steps per accumulator
-    long long S = div_up(148 * 2, (long long)groups * ci_tiles * co_tiles);
-    const long long min_s = div_up(m_out, (long long)MAX_ROWS_PER_CTA);
-    if (S < min_s) S = min_s;
-    const long long max_s = div_up(m_out, WINR);
-    if (S > max_s) S = max_s;
-    if (S < 1) S = 1;
+    // Row slices (split-K): one CTA per SM at a time, so the launch costs waves x (rows per CTA + a fixed prologue /
+    // epilogue); pick the slice count that minimises it -- a grid of 2.5 waves wastes half a wave.
+    const long long per_slice = (long long)groups * ci_tiles * co_tiles;
+    const long long min_s = std::max<long long>(1, div_up(m_out, (long long)MAX_ROWS_PER_CTA));
+    const long long max_s = std::max<long long>(min_s, std::min<long long>(div_up(m_out, WINR), div_up(148 * 6, per_slice)));
+    long long S = min_s, best = -1;
+    for (long long s = min_s; s <= max_s; ++s) {
+        const long long r = div_up(div_up(m_out, s), WINR) * WINR, ctas = div_up(m_out, r) * per_slice;
+        const long long cost = div_up(ctas, 148) * (r + 384);          // 384 rows ~ prologue (zero fill) + epilogue (TMEM -> atomics)
+        if (best < 0 || cost < best) { best = cost; S = s; }
+    }
     long long rows = div_up(div_up(m_out, S), WINR) * WINR;
     S = div_up(m_out, rows);
     CPD_REQUIRE(S <= 65535, CPD_ERR_UNSUPPORTED, "tcgen05 wgrad: too many row slices");

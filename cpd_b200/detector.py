@@ -75,7 +75,7 @@ class CPDHotPathDetector(nn.Module):
         valid (host tensors, or device tensors whose producers have finished).  Pass the result to forward()."""
         device = next(self.parameters()).device
         if self._side is None:
-            self._side = torch.cuda.Stream(device=device)
+            self._side = torch.cuda.Stream(device=device, priority=-1)   # high priority: its small kernels must not starve behind the backward
         with torch.cuda.stream(self._side):
             bd = self._input_stage(batch, device, plan=True)
             ev = torch.cuda.Event()

@@ -182,21 +182,34 @@ def tc_wgrad_ok(cin, K, cout):
     return cin >= 8 and cin % 8 == 0 and ((cin <= 256 and 256 % cin == 0) or cin % 256 == 0) and cout >= 8 and cout % 8 == 0 and K <= 64
 
 
-def split_rows(x):
+def split_rows(x, colsum=False):
     """Split-row image of a row matrix (m, c), c % 8 == 0: (m, 2, c) bf16, row = [hi(c) | lo(c)] -- the operand
-    format of the tcgen05 kernels (include/cpd_b200.h).  Returns None when the layout does not apply."""
+    format of the tcgen05 kernels (include/cpd_b200.h).  Returns None when the layout does not apply.
+    colsum=True (c a power of two): returns (image, per-channel column sums of x) from the same pass."""
     _need_cuda(x)
     if x.dim() != 2 or x.shape[1] % 8 or x.shape[1] < 8:
-        return None
+        return (None, None) if colsum else None
     L = _lib.lib()
     x = _f32c(x)
-    xs = torch.empty((x.shape[0], 2, x.shape[1]), dtype=torch.bfloat16, device=x.device)
-    _lib.check(L.cpd_split_rows(_ptr(x), x.shape[0], x.shape[1], _ptr(xs), _stream()), "cpd_split_rows")
-    return xs
+    c = x.shape[1]
+    xs = torch.empty((x.shape[0], 2, c), dtype=torch.bfloat16, device=x.device)
+    cs = torch.empty((c,), dtype=torch.float32, device=x.device) if colsum and c <= 2048 and c & (c - 1) == 0 else None
+    _lib.check(L.cpd_split_rows(_ptr(x), x.shape[0], c, _ptr(xs), _ptr(cs), _stream()), "cpd_split_rows")
+    return (xs, cs) if colsum else xs
+
+
+def tile_tap_masks(nbr):
+    """Per 128-row tile of a (m, K <= 32) neighbour table: bitmask of the taps that have a neighbour in the tile."""
+    _need_cuda(nbr)
+    L = _lib.lib()
+    m, K = nbr.shape
+    masks = torch.empty(((m + 127) // 128,), dtype=torch.int32, device=nbr.device)
+    _lib.check(L.cpd_tile_tap_masks(_ptr(nbr), m, K, _ptr(masks), _stream()), "cpd_tile_tap_masks")
+    return masks
 
 
 def gather_gemm(x, w, nbr, bias=None, scale=None, shift=None, residual=None, relu=False, stats=None,
-                algo=ALGO_AUTO, out=None, x_split=None):
+                algo=ALGO_AUTO, out=None, x_split=None, tile_masks=None):
     """y[o] = epi(sum_k W[:,k,:] x[nbr[o,k]]);  w is (cout, K, cin) (any (cout, ..., cin) view).
     x_split: split_rows(x) if the caller already has it (shared between forward and weight-gradient)."""
     _need_cuda(x, w, nbr)
@@ -216,7 +229,8 @@ def gather_gemm(x, w, nbr, bias=None, scale=None, shift=None, residual=None, rel
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    _lib.check(L.cpd_gather_gemm(_ptr(x), _ptr(x_split), x.shape[0], cin, _ptr(w), K, cout, _ptr(nbr), m_out, _ptr(bias),
+    assert tile_masks is None or tile_masks.numel() == (m_out + 127) // 128
+    _lib.check(L.cpd_gather_gemm(_ptr(x), _ptr(x_split), x.shape[0], cin, _ptr(w), K, cout, _ptr(nbr), _ptr(tile_masks), m_out, _ptr(bias),
                                  _ptr(scale), _ptr(shift), _ptr(residual), int(bool(relu)), _ptr(stats), _ptr(y), int(algo),
                                  _ptr(ws), wsb, _stream()), "cpd_gather_gemm")
     if PROFILE is not None:

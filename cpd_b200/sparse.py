@@ -36,12 +36,42 @@ class Rulebook:
         self.ksize, self.stride, self.padding = ksize, stride, padding
         self.out_hash = None                # coordinate hash of out_coords (strided only)
         self._nbr_fwd_t = None              # (K, m_out) transposed table for the weight-gradient kernel
+        self._masks_fwd = None              # per-tile tap masks of nbr_fwd (k-block skipping in the tcgen05 kernel)
+        self._bwd_sorted = None             # strided: (nbr_bwd rows grouped by tap pattern, inverse permutation, tile masks)
 
     @property
     def nbr_fwd_t(self):
         if self._nbr_fwd_t is None:
             self._nbr_fwd_t = self.nbr_fwd.t().contiguous()
         return self._nbr_fwd_t
+
+    @property
+    def masks_fwd(self):
+        """Tile tap masks of the forward table; only worth it for 3-D kernels (z-boundary tiles lose whole taps)."""
+        if self.nbr_fwd.shape[1] != 27 or self.nbr_fwd.shape[0] == 0:
+            return None
+        if self._masks_fwd is None:
+            self._masks_fwd = ops.tile_tap_masks(self.nbr_fwd)
+        return self._masks_fwd
+
+    def bwd_sorted(self):
+        """Input-gradient table of a STRIDED conv with its rows grouped by tap pattern.  An input site feeds outputs only
+        through the taps matching its coordinate parity (<= 8 of 27 for stride 2), but a tile in spatial order mixes all
+        parities and would run every tap; grouped, each 128-row tile keeps its own few taps and the kernel skips the rest.
+        Returns (table, inverse permutation, tile masks) or None when it does not apply."""
+        nb = self.nbr_bwd
+        if nb is None or nb.shape[1] < 4 or nb.shape[1] > 27 or nb.shape[0] == 0 or all(int(s) == 1 for s in self.stride):
+            return None
+        if self._bwd_sorted is None:
+            K = nb.shape[1]
+            weights = torch.ones(K, dtype=torch.int64, device=nb.device) << torch.arange(K, dtype=torch.int64, device=nb.device)
+            key = ((nb >= 0).to(torch.int64) * weights).sum(1)
+            perm = torch.argsort(key, stable=True)
+            inv = torch.empty_like(perm)
+            inv[perm] = torch.arange(perm.numel(), dtype=perm.dtype, device=perm.device)
+            nbs = nb.index_select(0, perm).contiguous()
+            self._bwd_sorted = (nbs, inv, ops.tile_tap_masks(nbs))
+        return self._bwd_sorted
 
 
 class SparseConvTensor:
@@ -128,7 +158,7 @@ class _GatherConv(torch.autograd.Function):
         if algo != ops.ALGO_SIMT and (ops.tc_gemm_ok(cin, K, cout) or (needs_grad and ops.tc_wgrad_ok(cin, K, cout))):
             xs = ops.split_rows(x)
         ctx.xs = xs if needs_grad else None
-        y = ops.gather_gemm(x, weight, rb.nbr_fwd, bias=bias, stats=stats, algo=algo, x_split=xs)
+        y = ops.gather_gemm(x, weight, rb.nbr_fwd, bias=bias, stats=stats, algo=algo, x_split=xs, tile_masks=rb.masks_fwd)
         if not want_stats:
             return y
         ctx.mark_non_differentiable(stats)
@@ -154,23 +184,34 @@ class _GatherConv(torch.autograd.Function):
                 dw, db = dwp[:cout].reshape(weight.shape), (dbp[:cout] if dbp is not None else None)
             return dx, dw, db, None, None, None
         # one split-row image of dy serves the input-gradient GEMM and the weight-gradient
-        dys = None
+        dys = db_fused = None
         if ctx.algo != ops.ALGO_SIMT and ((ctx.needs_input_grad[0] and ops.tc_gemm_ok(cout, K, cin)) or
                                           (want_w and ops.tc_wgrad_ok(cin, K, cout))):
-            dys = ops.split_rows(dy)
+            if ctx.has_bias:
+                dys, db_fused = ops.split_rows(dy, colsum=True)          # the bias gradient falls out of the same pass
+            else:
+                dys = ops.split_rows(dy)
         if ctx.needs_input_grad[0]:
             if rb.kind == "subm":
                 wt = ops.weight_transpose(weight, flip_taps=True)
-                dx = ops.gather_gemm(dy, wt, rb.nbr_fwd, algo=ctx.algo, x_split=dys)
+                dx = ops.gather_gemm(dy, wt, rb.nbr_fwd, algo=ctx.algo, x_split=dys, tile_masks=rb.masks_fwd)
             else:
                 wt = ops.weight_transpose(weight, flip_taps=False)
-                dx = ops.gather_gemm(dy, wt, rb.nbr_bwd, algo=ctx.algo, x_split=dys)
+                grouped = rb.bwd_sorted() if dys is not None else None
+                if grouped is not None:
+                    nbs, inv, masks = grouped
+                    dx = ops.gather_gemm(dy, wt, nbs, algo=ctx.algo, x_split=dys, tile_masks=masks).index_select(0, inv)
+                else:
+                    dx = ops.gather_gemm(dy, wt, rb.nbr_bwd, algo=ctx.algo, x_split=dys)
         if want_w:
+            wb = ctx.has_bias and db_fused is None
             if rb.nbr_fwd.shape[1] > 1:
-                dw, db = ops.gather_wgrad(x, dy, rb.nbr_fwd_t, want_bias=ctx.has_bias, tap_major=True, x_split=ctx.xs, dy_split=dys)
+                dw, db = ops.gather_wgrad(x, dy, rb.nbr_fwd_t, want_bias=wb, tap_major=True, x_split=ctx.xs, dy_split=dys)
             else:
-                dw, db = ops.gather_wgrad(x, dy, rb.nbr_fwd, want_bias=ctx.has_bias, x_split=ctx.xs, dy_split=dys)
+                dw, db = ops.gather_wgrad(x, dy, rb.nbr_fwd, want_bias=wb, x_split=ctx.xs, dy_split=dys)
             dw = dw.view_as(weight)
+            if db_fused is not None:
+                db = db_fused
         ctx.xs = None
         return dx, dw, db, None, None, None
 

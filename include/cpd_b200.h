@@ -133,12 +133,20 @@ enum cpd_gemm_algo { CPD_ALGO_AUTO = 0, CPD_ALGO_SIMT = 1, CPD_ALGO_TCGEN05 = 2 
  * cpd_gather_gemm / cpd_gather_wgrad build the images they need in their workspace unless the caller
  * passes one it already has (x_split / dy_split != NULL): forward and weight-gradient share the image
  * of x, input-gradient and weight-gradient share the image of dy. */
-CPD_API int32_t cpd_split_rows(const float *x, int64_t m, int32_t c, void *xs, cpd_stream_t stream);
+/* colsum (NULL ok; c a power of two <= 2048): overwritten with the per-channel column sums of x, accumulated while the
+ * rows stream through -- with x = dy this is the bias gradient, for free. */
+CPD_API int32_t cpd_split_rows(const float *x, int64_t m, int32_t c, void *xs, float *colsum, cpd_stream_t stream);
+
+/* Per 128-row tile of a neighbour table (m, K <= 32): bit k of masks[tile] = some row of the tile has a
+ * neighbour at tap k.  masks: ceil(m / 128) uint32.  Computed once per rulebook (it only depends on the
+ * table) and passed to cpd_gather_gemm, whose tensor-core kernel then skips the k-blocks of absent taps. */
+CPD_API int32_t cpd_tile_tap_masks(const int32_t *nbr, int64_t m, int32_t K, uint32_t *masks, cpd_stream_t stream);
 
 /* x_split (NULL ok): split-row image of x (cpd_split_rows); have_x_split tells the workspace query
- * whether the call will pass one. */
+ * whether the call will pass one.  tile_masks (NULL ok): cpd_tile_tap_masks(nbr). */
 CPD_API int32_t cpd_gather_gemm(const float *x, const void *x_split, int64_t m_in, int32_t cin, const float *w,
-                        int32_t K, int32_t cout, const int32_t *nbr, int64_t m_out, const float *bias,
+                        int32_t K, int32_t cout, const int32_t *nbr, const uint32_t *tile_masks, int64_t m_out,
+                        const float *bias,
                         const float *scale, const float *shift, const float *residual, int32_t relu,
                         float *stats, float *y, int32_t algo, void *ws, size_t ws_bytes, cpd_stream_t stream);
 CPD_API size_t cpd_gather_gemm_workspace_bytes(int64_t m_in, int64_t m_out, int32_t cin, int32_t K, int32_t cout,

@@ -186,3 +186,22 @@ def test_detector_train_step_and_eval(cuda, oracle):
     t = det.last_batch_dict["encoded_spconv_tensor"]
     assert np.array_equal(t.indices.cpu().numpy(), coords)
     assert float(np.abs(t.features.cpu().numpy() - feats).max()) <= TOL * max(1.0, float(np.abs(feats).max()))
+
+
+def test_prepared_input_stage_matches_inline(cuda):
+    """detector.prepare (voxelize + tower plans on a side stream, one step ahead) feeds the same step as the inline path."""
+    from cpd_b200 import detector
+    torch.manual_seed(0)
+    det = detector.CPDHotPathDetector().to(cuda).train()
+    batch = _batch(cuda, 2, 20000, seed0=40)
+    loss0, _ = det(batch)
+    enc0 = det.last_batch_dict["encoded_spconv_tensor"]
+    prep = det.prepare(batch)
+    assert "tower_plan" in prep and "tower_plan1" in prep
+    loss1, _ = det(batch, prepared=prep)
+    enc1 = det.last_batch_dict["encoded_spconv_tensor"]
+    assert torch.equal(enc0.indices, enc1.indices)
+    assert float((enc0.features - enc1.features).abs().max()) <= 1e-4 * max(1.0, float(enc0.features.abs().max()))
+    assert abs(float(loss0) - float(loss1)) <= 1e-4 * max(1.0, abs(float(loss0)))
+    loss1.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in det.parameters())

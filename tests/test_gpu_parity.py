@@ -338,3 +338,77 @@ def test_fused_bn_train_matches_torch(cuda, m, c, relu, res):
     assert float((bn.running_mean.double().cpu() - ref.running_mean).abs().max()) <= 1e-5
     assert float((bn.running_var.double().cpu() - ref.running_var).abs().max()) <= 1e-5
     assert int(bn.num_batches_tracked) == 1
+
+
+# ------------------------------------------------------------------------------- tcgen05 operand format + scheduling aids
+def test_split_rows_image_is_the_rn_bf16_split(cuda):
+    """cpd_split_rows: hi = RN_bf16(x), lo = RN_bf16(x - hi), bit-exact; column sums from the same pass."""
+    from cpd_b200 import ops
+    torch.manual_seed(5)
+    for m, c in ((1, 8), (777, 16), (4099, 32), (3000, 128), (513, 40)):
+        x = torch.randn(m, c, device=cuda) * torch.logspace(-3, 3, c, device=cuda)
+        x[0, 0] = 0.0
+        xs, cs = ops.split_rows(x, colsum=True)
+        hi = x.to(torch.bfloat16)
+        lo = (x - hi.float()).to(torch.bfloat16)
+        assert xs.shape == (m, 2, c)
+        assert torch.equal(xs[:, 0, :].view(torch.int16), hi.view(torch.int16))
+        assert torch.equal(xs[:, 1, :].view(torch.int16), lo.view(torch.int16))
+        rec = xs[:, 0, :].float() + xs[:, 1, :].float()
+        assert float(((rec - x).abs() / x.abs().clamp_min(1e-30)).max()) <= 2.0 ** -15      # x = hi + lo to ~2^-16
+        if c & (c - 1) == 0:
+            ref = x.double().sum(0)
+            assert float((cs.double() - ref).abs().max()) <= 1e-4 * max(1.0, float(x.abs().sum(0).max()))
+        else:
+            assert cs is None
+    assert ops.split_rows(torch.randn(5, 5, device=cuda)) is None         # needs c % 8 == 0
+
+
+def test_tile_tap_masks_and_kblock_skipping_are_exact(cuda):
+    """Tile masks only skip work that multiplies zero rows: results are bit-identical with and without them,
+    also for a strided input-gradient table whose rows were grouped by tap pattern."""
+    from cpd_b200 import ops
+    torch.manual_seed(6)
+    m_in, m_out, cin, cout, K = 5000, 3333, 32, 64, 27
+    nbr = torch.randint(0, m_in, (m_out, K), device=cuda, dtype=torch.int32)
+    nbr[torch.rand(m_out, K, device=cuda) > 0.3] = -1
+    nbr[:512, 9:] = -1                       # whole tiles without taps 9..26
+    nbr[1024:1152] = -1                      # an empty tile
+    masks = ops.tile_tap_masks(nbr)
+    valid = (nbr >= 0)
+    for t in range((m_out + 127) // 128):
+        bits = valid[128 * t:128 * (t + 1)].any(0).cpu().numpy()
+        assert int(masks[t].item()) & 0xffffffff == sum(1 << k for k in range(K) if bits[k])
+    x = torch.randn(m_in, cin, device=cuda)
+    w = torch.randn(cout, K, cin, device=cuda) * 0.05
+    y0 = ops.gather_gemm(x, w, nbr, algo=ops.ALGO_TCGEN05)
+    y1 = ops.gather_gemm(x, w, nbr, algo=ops.ALGO_TCGEN05, tile_masks=masks)
+    assert torch.equal(y0, y1)
+    assert float(y1[1024:1152].abs().max()) == 0.0
+    ref = ops.gather_gemm(x, w, nbr, algo=ops.ALGO_SIMT)
+    assert float((y1 - ref).abs().max()) <= TOL * max(1.0, float(ref.abs().max()))
+    # rows grouped by tap pattern, results scattered back
+    key = (valid.long() << torch.arange(K, device=cuda)).sum(1)
+    perm = torch.argsort(key, stable=True)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(m_out, device=cuda)
+    nbs = nbr[perm].contiguous()
+    y2 = ops.gather_gemm(x, w, nbs, algo=ops.ALGO_TCGEN05, tile_masks=ops.tile_tap_masks(nbs))[inv]
+    assert float((y2 - y0).abs().max()) <= 2e-6 * max(1.0, float(y0.abs().max()))
+
+
+def test_shared_split_images_give_the_same_results(cuda):
+    from cpd_b200 import ops
+    torch.manual_seed(7)
+    m, cin, cout, K = 4000, 64, 32, 27
+    nbr = torch.randint(-m, m, (m, K), device=cuda, dtype=torch.int32).clamp_(min=-1)
+    x, dy = torch.randn(m, cin, device=cuda), torch.randn(m, cout, device=cuda)
+    w = torch.randn(cout, K, cin, device=cuda) * 0.05
+    xs, (dys, db) = ops.split_rows(x), ops.split_rows(dy, colsum=True)
+    assert torch.equal(ops.gather_gemm(x, w, nbr), ops.gather_gemm(x, w, nbr, x_split=xs))
+    nbr_t = nbr.t().contiguous()
+    dw0, db0 = ops.gather_wgrad(x, dy, nbr_t, want_bias=True, tap_major=True)
+    dw1, _ = ops.gather_wgrad(x, dy, nbr_t, tap_major=True, x_split=xs, dy_split=dys)
+    scale = max(1.0, float(dw0.abs().max()))
+    assert float((dw0 - dw1).abs().max()) <= 1e-5 * scale                 # split-K atomics: order differs run to run
+    assert float((db0 - db).abs().max()) <= 1e-4 * max(1.0, float(db0.abs().max()))
