@@ -25,12 +25,12 @@ SIGNATURES = {
     "cpd_rulebook_strided_tables": (_i32, [_vp, _i64, _vp, _vp, _sz, _vp, _i64, _vp, _vp, _sz, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cpd_split_rows": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "cpd_tile_tap_masks": (_i32, [_vp, _i64, _i32, _vp, _vp]),
-    "cpd_gather_gemm": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "cpd_gather_gemm": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
     "cpd_gather_gemm_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32, _i32, _i32, _i32]),
     "cpd_gather_wgrad": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
     "cpd_gather_wgrad_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32, _i32, _i32, _i32]),
-    "cpd_bn_train_fwd": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _f, _f, _vp, _vp, _vp, _vp, _vp]),
-    "cpd_bn_train_bwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "cpd_bn_train_fwd": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cpd_bn_train_bwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "cpd_weight_transpose": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "cpd_conv2d_table": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "cpd_sparse_to_dense": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp]),

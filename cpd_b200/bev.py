@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 from . import iou3d_nms_utils, ops
 from .backbone import _cfg
-from .sparse import Rulebook, _BNTrain, _GatherConv, bn_fusable, fold_bn
+from .sparse import Rulebook, _GatherConv, bn_fusable, bn_train, fold_bn
 
 
 class DenseMap:
@@ -93,7 +93,7 @@ class DenseConv2d(nn.Module):
         """Training: conv emitting batch statistics, then one fused normalise(+ReLU) pass."""
         rb, ho, wo = pixel_tables(x.n, x.h, x.w, self.k, self.k, self.stride, self.padding, x.data.device)
         y, stats = _GatherConv.apply(x.data, self.w_kc().contiguous(), self.bias, rb, self.algo, True)
-        return DenseMap(_BNTrain.apply(y, stats, bn.weight, bn.bias, None, bn, relu), x.n, ho, wo)
+        return DenseMap(bn_train(y, stats, bn, relu, dx_split=self.bias is None), x.n, ho, wo)
 
 
 class DenseConvTranspose2d(nn.Module):

@@ -9,7 +9,10 @@
 //   y  = relu?( (x - mean) * invstd * gamma + beta (+ residual) )
 //   dz = dy * (y > 0)?          dbeta = sum dz        dgamma = sum dz * xhat
 //   dx = gamma * invstd * (dz - dbeta / M - xhat * dgamma / M)          dresidual = dz
-#include "common.cuh"
+// Both streaming passes can also emit the split-row image (bf16 hi | lo, split.cu) of what they write: the
+// next convolution (forward) / the previous one (backward) consumes exactly that tensor, so the image costs
+// 4 extra bytes written per element instead of a separate read + write pass.
+#include "tc_common.cuh"
 
 namespace cpd {
 namespace {
@@ -40,7 +43,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_finalize_kernel(const float *__
 __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float *__restrict__ x, const float *__restrict__ mean_invstd,
                                                               const float *__restrict__ gamma, const float *__restrict__ beta,
                                                               const float *__restrict__ residual, int relu, long long m, int c,
-                                                              float *__restrict__ y)
+                                                              float *__restrict__ y, uint8_t *__restrict__ y_split)
 {
     extern __shared__ float sh[];   // scale[c], shift[c]
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
@@ -62,6 +65,13 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float *__res
         }
         if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         reinterpret_cast<float4 *>(y)[i] = v;
+        if (y_split) {                               // row image = hi(c) | lo(c) bf16, same 4c-byte pitch as the fp32 row
+            uint2 h, l;
+            tc::split4b(v, h, l);
+            uint8_t *p = y_split + (size_t)(i / (c / 4)) * (size_t)(4 * c) + (size_t)ch * 2;
+            *reinterpret_cast<uint2 *>(p) = h;
+            *reinterpret_cast<uint2 *>(p + 2 * c) = l;
+        }
     }
 }
 
@@ -116,7 +126,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float *_
                                                                   const float *__restrict__ dy, const float *__restrict__ mean_invstd,
                                                                   const float *__restrict__ gamma, const float *__restrict__ sums,
                                                                   int relu, long long m, int c, float *__restrict__ dx,
-                                                                  float *__restrict__ dres)
+                                                                  uint8_t *__restrict__ dx_split, float *__restrict__ dres)
 {
     extern __shared__ float sh[];   // a[c] = gamma*invstd, b[c] = dbeta/M, d[c] = invstd*dgamma/M, mu[c], is[c]
     const float inv_m = 1.f / (float)m;
@@ -145,6 +155,13 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float *_
         o.z = sh[ch + 2] * (g.z - sh[c + ch + 2] - (xv.z - sh[3 * c + ch + 2]) * sh[4 * c + ch + 2] * sh[2 * c + ch + 2]);
         o.w = sh[ch + 3] * (g.w - sh[c + ch + 3] - (xv.w - sh[3 * c + ch + 3]) * sh[4 * c + ch + 3] * sh[2 * c + ch + 3]);
         reinterpret_cast<float4 *>(dx)[i] = o;
+        if (dx_split) {
+            uint2 h, l;
+            tc::split4b(o, h, l);
+            uint8_t *p = dx_split + (size_t)(i / (c / 4)) * (size_t)(4 * c) + (size_t)ch * 2;
+            *reinterpret_cast<uint2 *>(p) = h;
+            *reinterpret_cast<uint2 *>(p + 2 * c) = l;
+        }
     }
 }
 
@@ -165,26 +182,30 @@ using namespace cpd;
 extern "C" int32_t cpd_bn_train_fwd(const float *x, int64_t m, int32_t c, const float *stats, const float *gamma,
                                     const float *beta, const float *residual, int32_t relu, float eps, float momentum,
                                     float *running_mean, float *running_var, float *mean_invstd, float *y,
-                                    cpd_stream_t stream_)
+                                    void *y_split, cpd_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     CPD_REQUIRE(x && stats && mean_invstd && y && m >= 1 && c >= 4 && c % 4 == 0 && c <= MAX_C, CPD_ERR_BAD_ARG,
                 "cpd_bn_train_fwd: bad argument (need c %% 4 == 0, c <= %d, m >= 1)", MAX_C);
     CPD_REQUIRE((running_mean == nullptr) == (running_var == nullptr), CPD_ERR_BAD_ARG, "cpd_bn_train_fwd: running stats go together");
-    CPD_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)residual) & 15) == 0, CPD_ERR_MISALIGNED, "cpd_bn_train_fwd: 16-byte alignment");
+    CPD_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)residual | (uintptr_t)y_split) & 15) == 0, CPD_ERR_MISALIGNED, "cpd_bn_train_fwd: 16-byte alignment");
+    CPD_REQUIRE(!y_split || c % 8 == 0, CPD_ERR_UNSUPPORTED, "cpd_bn_train_fwd: the split-row image needs c %% 8 == 0");
     bn_finalize_kernel<<<(unsigned)div_up(c, BN_THREADS), BN_THREADS, 0, stream>>>(stats, m, c, eps, momentum, mean_invstd, running_mean, running_var);
-    bn_apply_kernel<<<stream_grid(m * (c / 4)), BN_THREADS, 2 * c * sizeof(float), stream>>>(x, mean_invstd, gamma, beta, residual, relu, m, c, y);
+    bn_apply_kernel<<<stream_grid(m * (c / 4)), BN_THREADS, 2 * c * sizeof(float), stream>>>(x, mean_invstd, gamma, beta, residual, relu, m, c, y,
+                                                                                            reinterpret_cast<uint8_t *>(y_split));
     count_launch(2);
     return launch_status("cpd_bn_train_fwd");
 }
 
 extern "C" int32_t cpd_bn_train_bwd(const float *x, const float *y, const float *dy, int64_t m, int32_t c,
                                     const float *mean_invstd, const float *gamma, int32_t relu, float *dx,
-                                    float *dresidual, float *dgamma_dbeta /* (2,c): dbeta, dgamma */, cpd_stream_t stream_)
+                                    void *dx_split, float *dresidual, float *dgamma_dbeta /* (2,c): dbeta, dgamma */,
+                                    cpd_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     CPD_REQUIRE(x && dy && mean_invstd && dx && dgamma_dbeta && (y || !relu) && m >= 1 && c >= 4 && c % 4 == 0 && c <= MAX_C,
                 CPD_ERR_BAD_ARG, "cpd_bn_train_bwd: bad argument");
+    CPD_REQUIRE(!dx_split || (c % 8 == 0 && ((uintptr_t)dx_split & 15) == 0), CPD_ERR_UNSUPPORTED, "cpd_bn_train_bwd: the split-row image needs c %% 8 == 0");
     CPD_CUDA(cudaMemsetAsync(dgamma_dbeta, 0, sizeof(float) * 2 * c, stream));
     int ctas = (int)(m / 512 > 0 ? (m / 512 < 148 * 4 ? m / 512 : 148 * 4) : 1);
     int rpc = (int)div_up(m, ctas);
@@ -193,7 +214,8 @@ extern "C" int32_t cpd_bn_train_bwd(const float *x, const float *y, const float 
         x, y, dy, mean_invstd, relu, m, c, rpc, dgamma_dbeta);
     (void)lanes_c;
     bn_bwd_apply_kernel<<<stream_grid(m * (c / 4)), BN_THREADS, 5 * c * sizeof(float), stream>>>(x, y, dy, mean_invstd, gamma, dgamma_dbeta,
-                                                                                              relu, m, c, dx, dresidual);
+                                                                                              relu, m, c, dx, reinterpret_cast<uint8_t *>(dx_split),
+                                                                                              dresidual);
     count_launch(2);
     return launch_status("cpd_bn_train_bwd");
 }

@@ -13,7 +13,7 @@ namespace cpd {
 int32_t split_rows(const float *x, int64_t m, int32_t c, void *xs, float *colsum, cudaStream_t stream);
 int32_t tile_tap_masks(const int32_t *nbr, int64_t m, int32_t K, uint32_t *masks, cudaStream_t stream);
 int32_t gather_gemm_tc(const void *xs, int32_t cin, const float *w, int32_t K, int32_t cout,
-                       const int32_t *nbr, const uint32_t *tile_masks, int64_t m_out, const float *bias, const float *scale, const float *shift,
+                       const int32_t *nbr, const uint32_t *tile_masks, const int32_t *out_rows, int64_t m_out, const float *bias, const float *scale, const float *shift,
                        const float *residual, int32_t relu, float *stats, float *y, void *ws, size_t ws_bytes,
                        cudaStream_t stream);
 size_t gather_gemm_tc_workspace(int32_t cin, int32_t K, int32_t cout);
@@ -347,7 +347,8 @@ extern "C" int32_t cpd_tile_tap_masks(const int32_t *nbr, int64_t m, int32_t K, 
 }
 
 extern "C" int32_t cpd_gather_gemm(const float *x, const void *x_split, int64_t m_in, int32_t cin, const float *w, int32_t K,
-                                   int32_t cout, const int32_t *nbr, const uint32_t *tile_masks, int64_t m_out, const float *bias, const float *scale,
+                                   int32_t cout, const int32_t *nbr, const uint32_t *tile_masks, const int32_t *out_rows,
+                                   int64_t m_out, const float *bias, const float *scale,
                                    const float *shift, const float *residual, int32_t relu, float *stats, float *y,
                                    int32_t algo, void *ws, size_t ws_bytes, cpd_stream_t stream_)
 {
@@ -377,9 +378,10 @@ extern "C" int32_t cpd_gather_gemm(const float *x, const void *x_split, int64_t 
             p += image_bytes(m_in, cin);
         }
         const size_t left = ws_bytes - (size_t)(p - reinterpret_cast<uint8_t *>(ws));
-        return gather_gemm_tc(xs, cin, w, K, cout, nbr, tile_masks, m_out, bias, scale, shift, residual, relu, stats, y, p, left, stream);
+        return gather_gemm_tc(xs, cin, w, K, cout, nbr, tile_masks, out_rows, m_out, bias, scale, shift, residual, relu, stats, y, p, left, stream);
     }
     CPD_REQUIRE(x, CPD_ERR_BAD_ARG, "cpd_gather_gemm: the SIMT kernel needs the fp32 rows");
+    CPD_REQUIRE(!out_rows, CPD_ERR_UNSUPPORTED, "cpd_gather_gemm: out_rows needs the tcgen05 kernel");
     if (stats) CPD_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)cout, stream));
     Epilogue ep{bias, scale, shift, residual, stats, relu};
     if (cout > 32) launch_gg<64, 64, 4, 4>(x, cin, w, K, cout, nbr, m_out, ep, y, stream);

@@ -94,6 +94,7 @@ struct TcArgs {
     const int32_t *nbr;         // (m_out, K)
     unsigned int *tile_counter; // dynamic tile scheduler (zeroed by weight_split_kernel)
     const uint32_t *tile_masks; // NULL ok: per 128-row tile, bit k = tap k has a neighbour in the tile (cpd_tile_tap_masks)
+    const int32_t *out_rows;    // NULL ok: row r of the table is written to y[out_rows[r]] (tables visited in a permuted order)
     float *stats, *y;
     long long m_out;
     int cin, K, cout, relu;
@@ -217,9 +218,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
             const int buf = ACC == 2 ? (ti & 1) : 0;
             mbar_wait(accf0 + 8 * buf, ACC == 2 ? ((ti >> 1) & 1) : (ti & 1));
             tc_fence_after();
-            const long long row = (t / ntn) * BM + warp * 32 + lane;
+            const long long trow = (t / ntn) * BM + warp * 32 + lane;      // row of the table / tile
             const int n0 = (int)(t % ntn) * BN;
-            const bool valid = row < a.m_out;
+            const bool valid = trow < a.m_out;
+            const long long row = (valid && a.out_rows) ? (long long)__ldg(a.out_rows + trow) : trow;   // row of y (and of the residual)
             const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 2 * BN);
 #pragma unroll
             for (int i = 0; i < BN / 16; ++i) {
@@ -543,7 +545,7 @@ int32_t tile_tap_masks(const int32_t *nbr, int64_t m, int32_t K, uint32_t *masks
 }
 
 int32_t gather_gemm_tc(const void *xs, int32_t cin, const float *w, int32_t K, int32_t cout, const int32_t *nbr,
-                       const uint32_t *tile_masks, int64_t m_out, const float *bias, const float *scale, const float *shift, const float *residual,
+                       const uint32_t *tile_masks, const int32_t *out_rows, int64_t m_out, const float *bias, const float *scale, const float *shift, const float *residual,
                        int32_t relu, float *stats, float *y, void *ws, size_t ws_bytes, cudaStream_t stream)
 {
     CPD_REQUIRE(gather_gemm_tc_supported(cin, K, cout), CPD_ERR_UNSUPPORTED, "tcgen05 gather-GEMM: unsupported shape");
@@ -556,7 +558,7 @@ int32_t gather_gemm_tc(const void *xs, int32_t cin, const float *w, int32_t K, i
     const long long chunks = (long long)n_kb * cout * 8;
     weight_split_kernel<<<(unsigned)div_up(chunks, 256), 256, 0, stream>>>(w, cout, Kf, n_kb, bn, wsplit, stats, tile_counter);
     count_launch();
-    TcArgs a{bias, scale, shift, residual, reinterpret_cast<const uint8_t *>(xs), wsplit, nbr, tile_counter, tile_masks, stats, y, m_out, cin, K, cout, relu};
+    TcArgs a{bias, scale, shift, residual, reinterpret_cast<const uint8_t *>(xs), wsplit, nbr, tile_counter, tile_masks, out_rows, stats, y, m_out, cin, K, cout, relu};
     switch (cout) {
         case 16: return launch_tc<16>(a, stream);
         case 32: return launch_tc<32>(a, stream);

@@ -38,8 +38,15 @@ __global__ void split_rows_kernel(const float *__restrict__ x, long long n_chunk
     }
     if (COLSUM) {
         const int c8 = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % c8_per_row);
+        // lanes l, l + c8_per_row, ... of a warp hold the same channels: butterfly them together first
+        for (int off = c8_per_row; off < 32; off <<= 1) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(&acc[c8 * 8 + j], s[j]);
+            for (int j = 0; j < 8; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], off);
+        }
+        if ((int)(threadIdx.x & 31) < c8_per_row) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(&acc[c8 * 8 + j], s[j]);
+        }
         __syncthreads();
         for (int i = threadIdx.x; i < 8 * c8_per_row; i += blockDim.x) atomicAdd(colsum + i, acc[i]);
     }
@@ -58,7 +65,8 @@ int32_t split_rows(const float *x, int64_t m, int32_t c, void *xs, float *colsum
     if (m == 0) return CPD_OK;
     const long long n_chunks = (long long)m * (c / 8);
     long long blocks = div_up(n_chunks, 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;          // grid-stride: 16 CTAs of 256 threads per SM (256 * blocks % (c / 8) == 0)
+    const long long cap = colsum ? 148 * 6 : 148 * 16;   // grid-stride CTAs of 256 threads (256 * blocks % (c / 8) == 0); fewer when
+    if (blocks > cap) blocks = cap;                      // every CTA ends with c global atomics
     if (colsum) split_rows_kernel<true><<<(unsigned)blocks, 256, (size_t)c * sizeof(float), stream>>>(x, n_chunks, c / 8, reinterpret_cast<uint8_t *>(xs), colsum);
     else split_rows_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(x, n_chunks, c / 8, reinterpret_cast<uint8_t *>(xs), nullptr);
     count_launch();

@@ -209,7 +209,7 @@ def tile_tap_masks(nbr):
 
 
 def gather_gemm(x, w, nbr, bias=None, scale=None, shift=None, residual=None, relu=False, stats=None,
-                algo=ALGO_AUTO, out=None, x_split=None, tile_masks=None):
+                algo=ALGO_AUTO, out=None, x_split=None, tile_masks=None, out_rows=None):
     """y[o] = epi(sum_k W[:,k,:] x[nbr[o,k]]);  w is (cout, K, cin) (any (cout, ..., cin) view).
     x_split: split_rows(x) if the caller already has it (shared between forward and weight-gradient)."""
     _need_cuda(x, w, nbr)
@@ -230,7 +230,9 @@ def gather_gemm(x, w, nbr, bias=None, scale=None, shift=None, residual=None, rel
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     assert tile_masks is None or tile_masks.numel() == (m_out + 127) // 128
-    _lib.check(L.cpd_gather_gemm(_ptr(x), _ptr(x_split), x.shape[0], cin, _ptr(w), K, cout, _ptr(nbr), _ptr(tile_masks), m_out, _ptr(bias),
+    assert out_rows is None or (out_rows.dtype == torch.int32 and out_rows.numel() == m_out and out_rows.is_contiguous())
+    _lib.check(L.cpd_gather_gemm(_ptr(x), _ptr(x_split), x.shape[0], cin, _ptr(w), K, cout, _ptr(nbr), _ptr(tile_masks), _ptr(out_rows),
+                                 m_out, _ptr(bias),
                                  _ptr(scale), _ptr(shift), _ptr(residual), int(bool(relu)), _ptr(stats), _ptr(y), int(algo),
                                  _ptr(ws), wsb, _stream()), "cpd_gather_gemm")
     if PROFILE is not None:
@@ -348,30 +350,33 @@ def nms_mask(boxes_sorted, thresh, rotated=True):
 # ------------------------------------------------------------------------------------
 # fused training-mode BatchNorm (+ReLU, + residual) on row matrices
 # ------------------------------------------------------------------------------------
-def bn_train_fwd(x, stats, gamma, beta, residual, relu, eps, momentum, running_mean, running_var):
-    """-> (y, mean_invstd (2,c)).  stats (2,c) = per-channel sum / sum of squares of x (from gather_gemm)."""
+def bn_train_fwd(x, stats, gamma, beta, residual, relu, eps, momentum, running_mean, running_var, want_split=False):
+    """-> (y, mean_invstd (2,c), split-row image of y | None).  stats (2,c) = per-channel sum / sum of squares of x
+    (from gather_gemm)."""
     _need_cuda(x, stats)
     L = _lib.lib()
     x = _f32c(x)
     m, c = x.shape
     y = torch.empty_like(x)
+    ys = torch.empty((m, 2, c), dtype=torch.bfloat16, device=x.device) if want_split and c % 8 == 0 else None
     mi = torch.empty((2, c), dtype=torch.float32, device=x.device)
     residual = _f32c(residual) if residual is not None else None
     _lib.check(L.cpd_bn_train_fwd(_ptr(x), m, c, _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(residual), int(bool(relu)),
                                   float(eps), float(momentum), _ptr(running_mean), _ptr(running_var), _ptr(mi), _ptr(y),
-                                  _stream()), "cpd_bn_train_fwd")
-    return y, mi
+                                  _ptr(ys), _stream()), "cpd_bn_train_fwd")
+    return y, mi, ys
 
 
-def bn_train_bwd(x, y, dy, mean_invstd, gamma, relu, want_residual):
-    """-> (dx, dresidual | None, dgamma, dbeta)."""
+def bn_train_bwd(x, y, dy, mean_invstd, gamma, relu, want_residual, want_split=False):
+    """-> (dx, dresidual | None, dgamma, dbeta, split-row image of dx | None)."""
     _need_cuda(x, dy)
     L = _lib.lib()
     dy = _f32c(dy)
     m, c = x.shape
     dx = torch.empty_like(x)
+    dxs = torch.empty((m, 2, c), dtype=torch.bfloat16, device=x.device) if want_split and c % 8 == 0 else None
     dres = torch.empty_like(x) if want_residual else None
     gb = torch.empty((2, c), dtype=torch.float32, device=x.device)
     _lib.check(L.cpd_bn_train_bwd(_ptr(x), _ptr(y), _ptr(dy), m, c, _ptr(mean_invstd), _ptr(gamma), int(bool(relu)), _ptr(dx),
-                                  _ptr(dres), _ptr(gb), _stream()), "cpd_bn_train_bwd")
-    return dx, dres, gb[1], gb[0]
+                                  _ptr(dxs), _ptr(dres), _ptr(gb), _stream()), "cpd_bn_train_bwd")
+    return dx, dres, gb[1], gb[0], dxs

@@ -58,7 +58,7 @@ class Rulebook:
         """Input-gradient table of a STRIDED conv with its rows grouped by tap pattern.  An input site feeds outputs only
         through the taps matching its coordinate parity (<= 8 of 27 for stride 2), but a tile in spatial order mixes all
         parities and would run every tap; grouped, each 128-row tile keeps its own few taps and the kernel skips the rest.
-        Returns (table, inverse permutation, tile masks) or None when it does not apply."""
+        Returns (table, output row of every table row, tile masks) or None when it does not apply."""
         nb = self.nbr_bwd
         if nb is None or nb.shape[1] < 4 or nb.shape[1] > 27 or nb.shape[0] == 0 or all(int(s) == 1 for s in self.stride):
             return None
@@ -67,10 +67,8 @@ class Rulebook:
             weights = torch.ones(K, dtype=torch.int64, device=nb.device) << torch.arange(K, dtype=torch.int64, device=nb.device)
             key = ((nb >= 0).to(torch.int64) * weights).sum(1)
             perm = torch.argsort(key, stable=True)
-            inv = torch.empty_like(perm)
-            inv[perm] = torch.arange(perm.numel(), dtype=perm.dtype, device=perm.device)
             nbs = nb.index_select(0, perm).contiguous()
-            self._bwd_sorted = (nbs, inv, ops.tile_tap_masks(nbs))
+            self._bwd_sorted = (nbs, perm.to(torch.int32), ops.tile_tap_masks(nbs))     # table row r computes dx[perm[r]]
         return self._bwd_sorted
 
 
@@ -153,10 +151,12 @@ class _GatherConv(torch.autograd.Function):
             return ops.gather_gemm(x, wp, rb.nbr_fwd, bias=bp, algo=algo)[:, :cout].contiguous()
         # the split-row image of x (bf16 hi | lo, the tcgen05 operand format) is built once and shared by the
         # forward GEMM and the weight-gradient
-        needs_grad = weight.requires_grad and torch.is_grad_enabled()
+        needs_grad = bool(ctx.needs_input_grad[1])          # (grad mode is off inside forward: ask the context)
         xs = None
         if algo != ops.ALGO_SIMT and (ops.tc_gemm_ok(cin, K, cout) or (needs_grad and ops.tc_wgrad_ok(cin, K, cout))):
-            xs = ops.split_rows(x)
+            xs = _carried_split(x)
+            if xs is None:
+                xs = ops.split_rows(x)
         ctx.xs = xs if needs_grad else None
         y = ops.gather_gemm(x, weight, rb.nbr_fwd, bias=bias, stats=stats, algo=algo, x_split=xs, tile_masks=rb.masks_fwd)
         if not want_stats:
@@ -190,7 +190,9 @@ class _GatherConv(torch.autograd.Function):
             if ctx.has_bias:
                 dys, db_fused = ops.split_rows(dy, colsum=True)          # the bias gradient falls out of the same pass
             else:
-                dys = ops.split_rows(dy)
+                dys = _carried_split(dy)                                 # written by the BatchNorm backward that produced dy
+                if dys is None:
+                    dys = ops.split_rows(dy)
         if ctx.needs_input_grad[0]:
             if rb.kind == "subm":
                 wt = ops.weight_transpose(weight, flip_taps=True)
@@ -198,9 +200,9 @@ class _GatherConv(torch.autograd.Function):
             else:
                 wt = ops.weight_transpose(weight, flip_taps=False)
                 grouped = rb.bwd_sorted() if dys is not None else None
-                if grouped is not None:
-                    nbs, inv, masks = grouped
-                    dx = ops.gather_gemm(dy, wt, nbs, algo=ctx.algo, x_split=dys, tile_masks=masks).index_select(0, inv)
+                if grouped is not None and ops.tc_gemm_ok(cout, K, cin):
+                    nbs, out_rows, masks = grouped                      # the epilogue scatters row r to dx[out_rows[r]]
+                    dx = ops.gather_gemm(dy, wt, nbs, algo=ctx.algo, x_split=dys, tile_masks=masks, out_rows=out_rows)
                 else:
                     dx = ops.gather_gemm(dy, wt, rb.nbr_bwd, algo=ctx.algo, x_split=dys)
         if want_w:
@@ -220,21 +222,44 @@ class _BNTrain(torch.autograd.Function):
     """Training-mode BatchNorm (+residual) (+ReLU) on a row matrix, statistics supplied by the conv epilogue."""
 
     @staticmethod
-    def forward(ctx, x, stats, gamma, beta, residual, bn, relu):
-        y, mi = ops.bn_train_fwd(x, stats, gamma, beta, residual, relu, bn.eps, bn.momentum if bn.momentum is not None else 0.1,
-                                 bn.running_mean if bn.track_running_stats else None,
-                                 bn.running_var if bn.track_running_stats else None)
+    def forward(ctx, x, stats, gamma, beta, residual, bn, relu, dx_split):
+        y, mi, ys = ops.bn_train_fwd(x, stats, gamma, beta, residual, relu, bn.eps, bn.momentum if bn.momentum is not None else 0.1,
+                                     bn.running_mean if bn.track_running_stats else None,
+                                     bn.running_var if bn.track_running_stats else None, want_split=True)
         if bn.track_running_stats and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
-        ctx.relu, ctx.has_res = relu, residual is not None
+        ctx.relu, ctx.has_res, ctx.dx_split = relu, residual is not None, dx_split
         ctx.save_for_backward(x, y if relu else None, mi, gamma)
-        return y
+        if ys is None:
+            ys = y.new_empty(0)
+        ctx.mark_non_differentiable(ys)
+        return y, ys
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _unused=None):
         x, y, mi, gamma = ctx.saved_tensors
-        dx, dres, dgamma, dbeta = ops.bn_train_bwd(x, y, dy, mi, gamma, ctx.relu, ctx.has_res)
-        return dx, None, (dgamma if gamma is not None else None), (dbeta if gamma is not None else None), dres, None, None
+        dx, dres, dgamma, dbeta, dxs = ops.bn_train_bwd(x, y, dy, mi, gamma, ctx.relu, ctx.has_res, want_split=ctx.dx_split)
+        if dxs is not None:
+            dx._cpd_split = dxs            # picked up by the producing convolution's backward (its dy)
+        return dx, None, (dgamma if gamma is not None else None), (dbeta if gamma is not None else None), dres, None, None, None
+
+
+def bn_train(y, stats, bn, relu, residual=None, dx_split=False):
+    """Fused training BatchNorm (+residual)(+ReLU).  The output carries the split-row image of itself (`_cpd_split`,
+    written by the same pass) for the convolution that consumes it; dx_split: the backward also emits the image of dx
+    for the convolution that produced y (worth it when that convolution has no bias gradient to take from its own split)."""
+    out, ys = _BNTrain.apply(y, stats, bn.weight, bn.bias, residual, bn, relu, dx_split)
+    if ys.numel():
+        out._cpd_split = ys
+    return out
+
+
+def _carried_split(t):
+    """The split-row image a producer attached to tensor t (bn_train / _BNTrain.backward), if it still matches."""
+    s = getattr(t, "_cpd_split", None)
+    if s is not None and t.dim() == 2 and s.shape[0] == t.shape[0] and s.shape[2] == t.shape[1] and s.device == t.device:
+        return s
+    return None
 
 
 def bn_fusable(bn):
@@ -328,7 +353,7 @@ class SparseConvolution(SparseModule):
         y, stats = _GatherConv.apply(x, w, self.bias, rb, self.algo, True)
         if y.shape[0] == 0:
             return self._wrap_output(inp, rb, out_hash, y)
-        feats = _BNTrain.apply(y, stats, bn.weight, bn.bias, residual, bn, relu)
+        feats = bn_train(y, stats, bn, relu, residual, dx_split=self.bias is None)
         return self._wrap_output(inp, rb, out_hash, feats)
 
     def forward_fused(self, inp, scale, shift, relu, residual=None):

@@ -143,10 +143,12 @@ CPD_API int32_t cpd_split_rows(const float *x, int64_t m, int32_t c, void *xs, f
 CPD_API int32_t cpd_tile_tap_masks(const int32_t *nbr, int64_t m, int32_t K, uint32_t *masks, cpd_stream_t stream);
 
 /* x_split (NULL ok): split-row image of x (cpd_split_rows); have_x_split tells the workspace query
- * whether the call will pass one.  tile_masks (NULL ok): cpd_tile_tap_masks(nbr). */
+ * whether the call will pass one.  tile_masks (NULL ok): cpd_tile_tap_masks(nbr).
+ * out_rows (NULL ok, tensor-core kernel only): a permutation of [0, m_out); row r of the table is written to
+ * y[out_rows[r]] -- for tables visited in a regrouped order (strided input-gradient grouped by tap pattern). */
 CPD_API int32_t cpd_gather_gemm(const float *x, const void *x_split, int64_t m_in, int32_t cin, const float *w,
-                        int32_t K, int32_t cout, const int32_t *nbr, const uint32_t *tile_masks, int64_t m_out,
-                        const float *bias,
+                        int32_t K, int32_t cout, const int32_t *nbr, const uint32_t *tile_masks,
+                        const int32_t *out_rows, int64_t m_out, const float *bias,
                         const float *scale, const float *shift, const float *residual, int32_t relu,
                         float *stats, float *y, int32_t algo, void *ws, size_t ws_bytes, cpd_stream_t stream);
 CPD_API size_t cpd_gather_gemm_workspace_bytes(int64_t m_in, int64_t m_out, int32_t cin, int32_t K, int32_t cout,
@@ -168,16 +170,18 @@ CPD_API size_t cpd_gather_wgrad_workspace_bytes(int64_t m_in, int64_t m_out, int
  * (cpd/models/backbones_3d/spconv_backbone.py:13-35,100-136,410; base_bev_backbone.py:31-59;
  * center_head.py:22-27,73-80).  stats (2, c) = per-channel sum and sum of squares of x as accumulated
  * by cpd_gather_gemm; mean_invstd (2, c) is written for the backward; running_* (NULL ok) follow
- * torch semantics (momentum, unbiased variance).  y = relu?((x-mean)*invstd*gamma+beta (+residual)). */
+ * torch semantics (momentum, unbiased variance).  y = relu?((x-mean)*invstd*gamma+beta (+residual)).
+ * y_split / dx_split (NULL ok, c % 8 == 0): also write the split-row image (cpd_split_rows format) of y / dx in the
+ * same pass -- the operand the next / previous convolution's tensor-core kernels gather from. */
 CPD_API int32_t cpd_bn_train_fwd(const float *x, int64_t m, int32_t c, const float *stats, const float *gamma,
                          const float *beta, const float *residual, int32_t relu, float eps, float momentum,
                          float *running_mean, float *running_var, float *mean_invstd, float *y,
-                         cpd_stream_t stream);
+                         void *y_split, cpd_stream_t stream);
 /* dz = dy*(y>0) if relu; dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)); dresidual (NULL ok) = dz;
  * dgamma_dbeta (2, c): row 0 = dbeta = sum dz, row 1 = dgamma = sum dz*xhat. */
 CPD_API int32_t cpd_bn_train_bwd(const float *x, const float *y, const float *dy, int64_t m, int32_t c,
                          const float *mean_invstd, const float *gamma, int32_t relu, float *dx,
-                         float *dresidual, float *dgamma_dbeta, cpd_stream_t stream);
+                         void *dx_split, float *dresidual, float *dgamma_dbeta, cpd_stream_t stream);
 
 /* (cout, K, cin) -> (cin, K, cout), optionally reversing the tap order (the operand of
  * the input-gradient: SubM reuses its own table with flipped taps). */

@@ -317,7 +317,12 @@ def test_fused_bn_train_matches_torch(cuda, m, c, relu, res):
     ref = torch.nn.BatchNorm1d(c, eps=1e-3, momentum=0.01).double().train()
     ref.load_state_dict({k: v.double().cpu() if v.is_floating_point() else v.cpu() for k, v in bn.state_dict().items()})
     stats = torch.stack([x.detach().sum(0), (x.detach() ** 2).sum(0)])            # what the conv epilogue would emit
-    y = sp._BNTrain.apply(x, stats, bn.weight, bn.bias, r, bn, relu)
+    y = sp.bn_train(x, stats, bn, relu, r, dx_split=True)
+    ys = sp._carried_split(y)                                                     # the same pass also wrote the bf16 hi | lo image of y
+    assert ys is not None
+    hi = y.detach().to(torch.bfloat16)
+    assert torch.equal(ys[:, 0, :].view(torch.int16), hi.view(torch.int16))
+    assert torch.equal(ys[:, 1, :].view(torch.int16), (y.detach() - hi.float()).to(torch.bfloat16).view(torch.int16))
     xr = x.detach().double().cpu().requires_grad_(True)
     rr = r.detach().double().cpu().requires_grad_(True) if res else None
     yr = ref(xr)
@@ -331,6 +336,9 @@ def test_fused_bn_train_matches_torch(cuda, m, c, relu, res):
     yr.backward(dy.double().cpu())
     sc = lambda t: max(1.0, float(t.abs().max()))
     assert float((x.grad.double().cpu() - xr.grad).abs().max()) <= TOL * sc(xr.grad)
+    dxs = sp._carried_split(x.grad)                                               # ... and the backward the image of dx
+    if dxs is not None:
+        assert torch.equal(dxs[:, 0, :].view(torch.int16), x.grad.to(torch.bfloat16).view(torch.int16))
     assert float((bn.weight.grad.double().cpu() - ref.weight.grad).abs().max()) <= TOL * sc(ref.weight.grad)
     assert float((bn.bias.grad.double().cpu() - ref.bias.grad).abs().max()) <= TOL * sc(ref.bias.grad)
     if res:
@@ -395,6 +403,9 @@ def test_tile_tap_masks_and_kblock_skipping_are_exact(cuda):
     nbs = nbr[perm].contiguous()
     y2 = ops.gather_gemm(x, w, nbs, algo=ops.ALGO_TCGEN05, tile_masks=ops.tile_tap_masks(nbs))[inv]
     assert float((y2 - y0).abs().max()) <= 2e-6 * max(1.0, float(y0.abs().max()))
+    # ... or scattered by the kernel's epilogue itself
+    y3 = ops.gather_gemm(x, w, nbs, algo=ops.ALGO_TCGEN05, tile_masks=ops.tile_tap_masks(nbs), out_rows=perm.to(torch.int32))
+    assert torch.equal(y3, y2)
 
 
 def test_shared_split_images_give_the_same_results(cuda):

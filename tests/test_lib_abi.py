@@ -38,7 +38,7 @@ def test_header_symbols_exported_and_bound():
 def test_bad_arguments_return_status_not_exit():
     from cpd_b200 import _lib
     L = _lib.lib()
-    st = L.cpd_gather_gemm(None, None, 0, 4, None, 27, 4, None, None, 10, None, None, None, None, 0, None, None, 0, None, 0, None)
+    st = L.cpd_gather_gemm(None, None, 0, 4, None, 27, 4, None, None, None, 10, None, None, None, None, 0, None, None, 0, None, 0, None)
     assert st == -1 and b"null" in L.cpd_last_error_string()
     with pytest.raises(_lib.CpdError):
         _lib.check(st, "cpd_gather_gemm")
