@@ -82,6 +82,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
 {
     constexpr int STAGES = w_stages(BN, AM), STAGE = w_stage_bytes(BN, AM);
     constexpr int A_BYTES = w_a_bytes(AM), B_BYTES = KB * BN * 2;
+    constexpr bool SWAP = BN == 256 && AM <= 64;     // narrow cout: the gathered tile is the M operand (see the MMA issuer)
+    static_assert(!SWAP || A_BYTES == 4096, "swapped roles expect one 64-column dY block per hi / lo tile");
     constexpr int A_C8 = AM / 8, A_V = (KB * A_C8 + NPROD - 1) / NPROD;        // 16-byte chunks per row / per thread per k-block
     constexpr int B_C8 = BN / 8, B_RSTEP = NPROD / B_C8, B_V = KB / B_RSTEP;   // chunks per row; row stride between a thread's chunks
     static_assert(NPROD % B_C8 == 0 && KB % B_RSTEP == 0, "B mapping");
@@ -215,7 +217,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
         }
         cp_async_wait_all();
         // ---- epilogue ----
-        if (n_blocks > 0) {
+        if (n_blocks > 0 && SWAP) {
+            // swapped roles: TMEM lane = (tap, ci) column of half h = warp / 4, accumulator columns = cout
+            mbar_wait(accum_bar, 0);
+            tc_fence_after();
+            const int h = warp >> 2, col = h * 128 + (warp & 3) * 32 + lane;
+            const int t = a.cin >= BN ? 0 : col / a.cin;
+            const int ci = a.cin >= BN ? ci0 + col : col % a.cin;
+            const bool live = t < T && ci < a.cin;
+            const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(h * 128);
+#pragma unroll 1
+            for (int c0 = 0; c0 < AM; c0 += 16) {
+                uint32_t u[16], v[16];
+                tmem_ld16(tacc + (uint32_t)c0, u);            // X_hi . dY_hi
+                tmem_ld16(tacc + (uint32_t)(64 + c0), v);     // X_hi . dY_lo + X_lo . dY_hi
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int co = co0 + c0 + j;          // consecutive lanes -> consecutive ci: coalesced reductions
+                        if (co < a.cout)
+                            atomicAdd(a.dw + ((size_t)co * a.K + tap0 + t) * a.cin + ci, __uint_as_float(u[j]) + __uint_as_float(v[j]));
+                    }
+                }
+            }
+        } else if (n_blocks > 0) {
             mbar_wait(accum_bar, 0);
             tc_fence_after();
             const int co = co0 + (warp & 3) * 32 + lane;      // warps w and w+4 share TMEM lanes and split the columns
@@ -247,6 +272,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
         // ================= MMA issuer =================
         constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                     ((uint32_t)((BN <= 128 ? 2 * BN : BN) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t IDESC_SW2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) |
+                                       ((uint32_t)(128 >> 4) << 24);      // swapped roles: N = [dY_hi | dY_lo] = 128
+        constexpr uint32_t IDESC_SW1 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
+                                       ((uint32_t)(128 >> 4) << 24);      // N = dY_hi = 64
         const uint32_t tiles_u32 = smem_u32(tiles);
         int it = 0;
         for (; it < n_blocks; ++it) {
@@ -267,7 +296,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
                 for (int k16 = 0; k16 < KB / 16; ++k16) {
                     if (k16 < (int)k16n) {
                         const uint64_t adv = (uint64_t)((k16 * 2048) >> 4);     // next 16-row K step (two 8-row atoms)
-                        if (BN <= 128) {
+                        if (SWAP) {
+                            // narrow cout: M = 128 lanes would be 3/4 (1/2) empty with dY as the A operand.  Swap the roles:
+                            // A = 128 gathered (tap, ci) columns (two halves of the X tile), B = [dY_hi | dY_lo] as ONE
+                            // N = 128 operand (its two 64-column blocks are adjacent) -> [main | corr], then X_lo . dY_hi
+                            // into corr: 4 narrow instructions (2 x (64 + 48) clk) instead of 3 N = 256 ones (3 x 128 clk).
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint64_t xh = b_hi + adv + (uint64_t)(h * (2 * 4096 >> 4)), xl = b_lo + adv + (uint64_t)(h * (2 * 4096 >> 4));
+                                const uint32_t d = tmem_base + (uint32_t)(h * 128);
+                                if (it == 0 && k16 == 0) umma_bf16_set(d, xh, a_hi, IDESC_SW2);
+                                else umma_bf16_acc(d, xh, a_hi + adv, IDESC_SW2);
+                                umma_bf16_acc(d + 64u, xl, a_hi + adv, IDESC_SW1);
+                            }
+                        } else if (BN <= 128) {
                             if (it == 0 && k16 == 0) umma_bf16_set(d_main, a_hi, b_hi, IDESC2);
                             else umma_bf16_acc(d_main, a_hi + adv, b_hi + adv, IDESC2);
                             umma_bf16_acc(d_corr, a_lo + adv, b_hi + adv, IDESC);
