@@ -31,6 +31,7 @@ class CPDHotPathDetector(nn.Module):
                  predict_boxes_when_training=True):
         super().__init__()
         self._side = None
+        self._held = (None, None)
         cfg = model_cfg or MODEL_CFG
         self.pc_range = [float(v) for v in pc_range]
         self.voxel_size = [float(v) for v in voxel_size]
@@ -83,22 +84,6 @@ class CPDHotPathDetector(nn.Module):
         bd["_ready"] = ev
         return bd
 
-    @staticmethod
-    def _adopt(obj, stream, seen):
-        """Tensors made on the side stream are consumed on `stream`: tell the caching allocator."""
-        if isinstance(obj, torch.Tensor):
-            if obj.is_cuda and id(obj) not in seen:
-                seen.add(id(obj))
-                obj.record_stream(stream)
-        elif isinstance(obj, dict):
-            for v in obj.values():
-                CPDHotPathDetector._adopt(v, stream, seen)
-        elif isinstance(obj, (list, tuple)):
-            for v in obj:
-                CPDHotPathDetector._adopt(v, stream, seen)
-        elif hasattr(obj, "__dict__") and not isinstance(obj, (torch.cuda.Event, nn.Module)):
-            CPDHotPathDetector._adopt(vars(obj), stream, seen)
-
     def forward(self, batch, prepared=None):
         """batch: dict(points=[...], points1=[...] (training, MM tower), gt_boxes=(B, M, 8) (training)).
         prepared: the result of prepare(batch) (optional).  Training returns (loss, tb_dict); eval returns
@@ -108,7 +93,12 @@ class CPDHotPathDetector(nn.Module):
             bd = prepared
             main = torch.cuda.current_stream(device)
             main.wait_event(bd.pop("_ready"))
-            self._adopt(bd, main, set())
+            # Tensors made on the side stream return to ITS allocator pool when freed, so they must outlive every kernel
+            # of this step on the main stream.  Rather than record_stream() on hundreds of tensors (which parks their
+            # blocks behind events and makes the side pool grow through cudaMalloc), the previous step's input stage is
+            # simply kept alive until this forward has been enqueued; the host sync at the end of forward (NMS count)
+            # then guarantees the step that used it has drained before its memory can be handed out again.
+            self._held = (self._held[1], dict(bd))
         else:
             bd = self._input_stage(batch, device, plan=False)
         bd = self.vfe(bd)
