@@ -174,7 +174,7 @@ PROFILE = None
 
 def tc_gemm_ok(cin, K, cout):
     """Shapes the tcgen05 gather-GEMM takes under ALGO_AUTO (mirrors cpd_gather_gemm's dispatch)."""
-    return cin % 8 == 0 and cin >= 8 and K <= 27 and (cout in (16, 32, 64, 128) or (cout % 256 == 0 and 0 < cout <= 2048))
+    return cin % 8 == 0 and cin >= 8 and K <= 27 and K * cin <= 8192 and (cout in (16, 32, 64, 128) or (cout % 256 == 0 and 0 < cout <= 2048))
 
 
 def tc_wgrad_ok(cin, K, cout):

@@ -64,3 +64,17 @@ def test_compat_namespace_resolves():
     spconv.SparseInverseConv3d(4, 4, 3, indice_key="k", bias=False)
     import numpy as np
     assert tv.from_numpy(np.zeros((2, 5), np.float32)).numpy().shape == (2, 5)
+
+
+def test_python_dispatch_predicates_mirror_the_library():
+    """ops.tc_gemm_ok / tc_wgrad_ok decide when the host code builds split-row images: they must agree with the
+    library's own dispatch (a workspace size > 0 means the tcgen05 kernel takes the shape)."""
+    from cpd_b200 import _lib, ops
+    L = _lib.lib()
+    for cin in (3, 5, 8, 16, 24, 32, 40, 64, 128, 256, 512):
+        for cout in (1, 3, 8, 16, 32, 48, 64, 128, 256, 512):
+            for K in (1, 4, 9, 27, 32):
+                lib_gemm = L.cpd_gather_gemm_workspace_bytes(1000, 900, cin, K, cout, 0, 1) > 0
+                assert ops.tc_gemm_ok(cin, K, cout) == lib_gemm, (cin, K, cout)
+                lib_wg = L.cpd_gather_wgrad_workspace_bytes(1000, 900, cin, K, cout, 0, 0) > 0
+                assert ops.tc_wgrad_ok(cin, K, cout) == lib_wg, (cin, K, cout)
