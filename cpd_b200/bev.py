@@ -302,6 +302,51 @@ def assign_targets_single(gt_boxes, num_classes, fmap_xy, stride, pc_range, voxe
     return heatmap, ret_boxes, inds, mask
 
 
+def assign_targets_batched(gt_boxes, num_classes, fmap_xy, stride, pc_range, voxel_size, num_max_objs=500,
+                           gaussian_overlap=0.1, min_radius=2, max_radius=24):
+    """assign_targets_single over a whole batch at once: gt_boxes (B, M, 8) -> heatmap (B, C, H, W), ret_boxes
+    (B, num_max_objs, 8), inds / mask (B, num_max_objs).  Same arithmetic, one set of launches instead of one per frame
+    (the forward pass is host-bound, every launch counts); the frame index is folded into the scatter index."""
+    W, H = int(fmap_xy[0]), int(fmap_xy[1])
+    dev = gt_boxes.device
+    gt = gt_boxes[:, :num_max_objs]
+    B, m = gt.shape[0], gt.shape[1]
+    heatmap = gt.new_zeros(B, num_classes, H, W)
+    ret_boxes = gt.new_zeros((B, num_max_objs, 8))
+    inds = torch.zeros((B, num_max_objs), dtype=torch.long, device=dev)
+    mask = torch.zeros((B, num_max_objs), dtype=torch.long, device=dev)
+    if m == 0 or B == 0:
+        return heatmap, ret_boxes, inds, mask
+    cx = ((gt[..., 0] - pc_range[0]) / voxel_size[0] / stride).clamp(min=0, max=W - 0.5)
+    cy = ((gt[..., 1] - pc_range[1]) / voxel_size[1] / stride).clamp(min=0, max=H - 0.5)
+    ix, iy = cx.int(), cy.int()
+    dx, dy = gt[..., 3] / voxel_size[0] / stride, gt[..., 4] / voxel_size[1] / stride
+    radius = torch.clamp_min(gaussian_radius(dx, dy, min_overlap=gaussian_overlap).int(), min_radius)
+    cls = gt[..., 7].long() - 1
+    valid = (dx > 0) & (dy > 0) & (cls >= 0) & (cls < num_classes)
+    radius = radius.clamp(max=max_radius)
+    R = max_radius
+    off = torch.arange(-R, R + 1, device=dev)
+    oy, ox = torch.meshgrid(off, off, indexing="ij")                         # (D, D)
+    sigma = (2 * radius + 1).float() / 6.0
+    g = torch.exp(-(ox * ox + oy * oy).float()[None, None] / (2 * sigma * sigma)[:, :, None, None])      # (B, m, D, D)
+    px, py = ix[:, :, None, None] + ox[None, None], iy[:, :, None, None] + oy[None, None]
+    rad = radius[:, :, None, None]
+    inside = (ox.abs()[None, None] <= rad) & (oy.abs()[None, None] <= rad) & (px >= 0) & (px < W) & (py >= 0) & (py < H) & \
+             valid[:, :, None, None]
+    frame = torch.arange(B, device=dev)[:, None, None, None]
+    flat = ((frame * num_classes + cls.clamp(0, num_classes - 1)[:, :, None, None]) * H + py.clamp(0, H - 1)) * W + px.clamp(0, W - 1)
+    vals = torch.where(inside, g, torch.zeros_like(g))
+    heatmap.view(-1).scatter_reduce_(0, flat.reshape(-1).long(), vals.reshape(-1), reduce="amax", include_self=True)
+    v = valid.long()
+    inds[:, :m] = (iy.long() * W + ix.long()) * v
+    mask[:, :m] = v
+    rb = torch.stack([cx - ix.float(), cy - iy.float(), gt[..., 2], gt[..., 3].clamp_min(1e-6).log(), gt[..., 4].clamp_min(1e-6).log(),
+                      gt[..., 5].clamp_min(1e-6).log(), torch.cos(gt[..., 6]), torch.sin(gt[..., 6])], dim=2)
+    ret_boxes[:, :m] = rb * valid[..., None].float()
+    return heatmap, ret_boxes, inds, mask
+
+
 def focal_loss_centernet(pred, gt):
     """loss_utils.py:265-302 (neg_loss_cornernet), without the host-side `if num_pos == 0` sync."""
     pos = gt.eq(1).float()
@@ -398,14 +443,12 @@ class CenterHead(nn.Module):
             local = torch.zeros(len(self.class_names) + 1, dtype=gt_boxes.dtype, device=gt_boxes.device)
             for j, nme in enumerate(names):
                 local[self.class_names.index(nme) + 1] = j + 1
-            per = []
-            for b in range(gt_boxes.shape[0]):
-                g = gt_boxes[b].clone()
-                g[:, -1] = local[g[:, -1].long().clamp(0, len(self.class_names))]
-                per.append(assign_targets_single(g, len(names), fm_xy, tcfg["FEATURE_MAP_STRIDE"], self.point_cloud_range,
-                                                 self.voxel_size, tcfg["NUM_MAX_OBJS"], tcfg["GAUSSIAN_OVERLAP"], tcfg["MIN_RADIUS"]))
+            g = gt_boxes.clone()
+            g[..., -1] = local[g[..., -1].long().clamp(0, len(self.class_names))]
+            per = assign_targets_batched(g, len(names), fm_xy, tcfg["FEATURE_MAP_STRIDE"], self.point_cloud_range, self.voxel_size,
+                                         tcfg["NUM_MAX_OBJS"], tcfg["GAUSSIAN_OVERLAP"], tcfg["MIN_RADIUS"])   # all frames at once
             for key, idx in (("heatmaps", 0), ("target_boxes", 1), ("inds", 2), ("masks", 3)):
-                ret[key].append(torch.stack([p[idx] for p in per], 0))
+                ret[key].append(per[idx])
         return ret
 
     def get_loss(self):

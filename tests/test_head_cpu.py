@@ -58,3 +58,22 @@ def test_state_dict_names_match_reference_layout():
     assert tuple(hs["heads_list.0.hm.1.weight"].shape) == (3, 64, 3, 3) and tuple(hs["heads_list.0.center_z.1.weight"].shape) == (1, 64, 3, 3)
     assert float(hs["heads_list.0.hm.1.bias"][0]) == np.float32(-2.19)
     assert "heads_list.0.dim.0.1.running_var" in hs
+
+
+def test_batched_target_assignment_equals_per_frame():
+    """assign_targets_batched (one set of launches for the whole batch) == assign_targets_single per frame, bit for bit."""
+    torch.manual_seed(3)
+    gt0 = torch.from_numpy(G["gt"])
+    frames = [gt0, gt0.flip(0).clone(), gt0.clone()]
+    frames[1][:, 0:2] += 3.7                                   # moved boxes
+    frames[2][10:, :] = 0                                      # padded frame (class 0 rows)
+    frames[2][3, 3] = 0.0                                      # a degenerate box
+    gt = torch.stack(frames, 0)
+    hb, rb, ib, mb = bev.assign_targets_batched(gt, 3, [188, 188], 8, RANGE, VS, 500, 0.1, 2)
+    for b in range(gt.shape[0]):
+        h1, r1, i1, m1 = bev.assign_targets_single(gt[b], 3, [188, 188], 8, RANGE, VS, 500, 0.1, 2)
+        assert torch.equal(hb[b], h1) and torch.equal(rb[b], r1) and torch.equal(ib[b], i1) and torch.equal(mb[b], m1)
+    e = bev.assign_targets_batched(gt[:, :0], 3, [188, 188], 8, RANGE, VS)
+    assert float(e[0].abs().sum()) == 0 and int(e[3].sum()) == 0 and tuple(e[0].shape) == (3, 3, 188, 188)
+    capped = bev.assign_targets_batched(gt, 3, [188, 188], 8, RANGE, VS, num_max_objs=7)
+    assert tuple(capped[1].shape) == (3, 7, 8) and int(capped[3].sum()) <= 21
