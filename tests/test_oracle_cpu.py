@@ -181,3 +181,25 @@ def test_nms_greedy_semantics(oracle):
     assert len(oracle.nms(b[:0], 0.5)) == 0 and oracle.nms(b[:1], 0.5).tolist() == [0]
     kn = oracle.nms(b, 0.5, rotated=False)
     assert 0 < len(kn) <= len(b)
+
+
+def test_bf16x3_split_error_model():
+    """The tensor-core kernels compute x.w as hi.hi + lo.hi + hi.lo with hi = RN_bf16(v), lo = RN_bf16(v - hi) (split.cu,
+    spconv_tc.cu).  Restated here with torch CPU bfloat16 (same round-to-nearest-even): the representation keeps
+    2^-16 of |v| and a 3456-term dot product (27 taps x 128 channels) stays within 1e-4 of its magnitude scale --
+    the bound DESIGN.md quotes, independent of the GPU."""
+    import torch
+    torch.manual_seed(0)
+    x = torch.randn(512, 3456) * torch.logspace(-2, 2, 3456)
+    w = torch.randn(3456, 64) / 3456 ** 0.5
+    split = lambda v: (v.to(torch.bfloat16), (v - v.to(torch.bfloat16).float()).to(torch.bfloat16))
+    xh, xl = split(x)
+    wh, wl = split(w)
+    rel = ((xh.float() + xl.float() - x).abs() / x.abs().clamp_min(1e-30)).max()
+    assert float(rel) <= 2.0 ** -16                                   # hi + lo carries 16+ mantissa bits
+    d = lambda a, b: a.double() @ b.double()                          # products of bf16 values are exact in fp64
+    got = d(xh, wh) + d(xl, wh) + d(xh, wl)                           # the lo.lo term is dropped, as in the kernels
+    ref = x.double() @ w.double()
+    scale = (x.abs().double() @ w.abs().double())                     # sum |x||w|: what the error is relative to
+    assert float(((got - ref).abs() / scale).max()) <= 3.0 * 2.0 ** -16
+    assert float((got - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
