@@ -40,6 +40,10 @@ def parse():
                                                             "(detector.prepare) instead of inline")
     a = ap.parse_args()
     a.no_prefetch = not a.prefetch
+    if a.prefetch:
+        # the side stream has its own caching-allocator pool; with the default allocator its growth (cudaMalloc per new
+        # segment size) made the first ~10 steps 1.5-2.5x slower -- expandable segments removed that (measured)
+        os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
     return a
 
 
