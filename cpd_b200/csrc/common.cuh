@@ -39,6 +39,38 @@ static inline int32_t launch_status(const char *what)
         }                                                                         \
     } while (0)
 
+// Function attributes (dynamic shared-memory opt-in) and the SM count are per DEVICE: a process that drives several
+// GPUs must configure each kernel on each of them.  One bit per device ordinal (< 64).
+struct PerDevice {
+    unsigned long long configured = 0ull;
+    int sms[64] = {0};
+};
+static inline int current_device()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev & 63;
+}
+static inline int device_sms(PerDevice &pd)
+{
+    const int dev = current_device();
+    if (!pd.sms[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        pd.sms[dev] = n;
+    }
+    return pd.sms[dev];
+}
+template <typename Kernel>
+static inline cudaError_t opt_in_smem(PerDevice &pd, Kernel k, size_t bytes)
+{
+    const int dev = current_device();
+    if (pd.configured >> dev & 1ull) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) pd.configured |= 1ull << dev;
+    return e;
+}
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -34,8 +34,9 @@ __global__ void hash_insert_kernel(const int32_t *__restrict__ coords, long long
     uint32_t s = hash_mix(key) & h.mask;
     for (;;) {
         uint32_t prev = atomicCAS(h.keys + s, HASH_EMPTY, key);
-        if (prev == HASH_EMPTY) { h.vals[s] = (int32_t)i; return; }
-        if (prev == key) { atomicMin(h.vals + s, (int32_t)i); return; }  // duplicate coordinate: keep the first row
+        // vals start at 0x7f7f7f7f (memset by the host wrapper); atomicMin in BOTH branches, so that a duplicate
+        // coordinate keeps its first row whatever the interleaving of the claiming and the later thread
+        if (prev == HASH_EMPTY || prev == key) { atomicMin(h.vals + s, (int32_t)i); return; }
         s = (s + 1) & h.mask;
     }
 }
@@ -236,7 +237,8 @@ extern "C" int32_t cpd_coord_hash_build(const int32_t *coords, int64_t m, const 
     if ((st = view_hash(hash, hash_bytes, &h, "cpd_coord_hash_build"))) return st;
     CPD_REQUIRE(m >= 0 && hash_bytes >= cpd_coord_hash_bytes(m), CPD_ERR_WORKSPACE, "cpd_coord_hash_build: hash buffer too small");
     CPD_REQUIRE(((uintptr_t)coords & 15) == 0, CPD_ERR_MISALIGNED, "cpd_coord_hash_build: coords must be 16-byte aligned");
-    CPD_CUDA(cudaMemsetAsync(hash, 0xff, hash_bytes / 2, stream));
+    CPD_CUDA(cudaMemsetAsync(hash, 0xff, hash_bytes / 2, stream));                              // keys: HASH_EMPTY
+    CPD_CUDA(cudaMemsetAsync((char *)hash + hash_bytes / 2, 0x7f, hash_bytes / 2, stream));      // vals: > any row index
     if (m > 0) {
         hash_insert_kernel<<<(unsigned)div_up(m, 256), 256, 0, stream>>>(coords, m, g, h);
         count_launch();

@@ -18,14 +18,10 @@ int32_t gather_gemm_tc(const void *xs, int32_t cin, const float *w, int32_t K, i
                        cudaStream_t stream);
 size_t gather_gemm_tc_workspace(int32_t cin, int32_t K, int32_t cout);
 bool gather_gemm_tc_supported(int32_t cin, int32_t K, int32_t cout);
-// two tcgen05 weight-gradient kernels: row-stationary with taps along N (wgrad_tc.cu, best for C_in <= 32, needs the
-// tap-major table) and per-tap pair lists (wgrad_pairs_tc.cu, best for C_in >= 64)
+// tcgen05 weight-gradient kernel: row-stationary with taps along N (wgrad_tc.cu; needs the tap-major table)
 bool gather_wgrad_rows_supported(int32_t cin, int32_t K, int32_t cout);
 int32_t gather_wgrad_rows_tc(const void *xs, int32_t cin, const void *dys, int64_t m_out, int32_t cout, const int32_t *nbr_t,
                              int32_t K, float *dw, cudaStream_t stream);
-bool gather_wgrad_pairs_supported(int32_t cin, int32_t K, int32_t cout);
-int32_t gather_wgrad_pairs_tc(const float *x, int32_t cin, const float *dy, int64_t m_out, int32_t cout, const int32_t *nbr,
-                              int32_t K, int32_t tap_major, float *dw, cudaStream_t stream);
 
 namespace {
 
@@ -365,8 +361,9 @@ extern "C" int32_t cpd_gather_gemm(const float *x, const void *x_split, int64_t 
         CPD_REQUIRE(ws && ws_bytes >= need, CPD_ERR_WORKSPACE, "cpd_gather_gemm: workspace too small (cpd_gather_gemm_workspace_bytes)");
         tc = true;
     } else if (algo == CPD_ALGO_AUTO) {
-        static const int min_cin = getenv("CPD_TC_MIN_CIN") ? atoi(getenv("CPD_TC_MIN_CIN")) : 8;   // tuning knob
-        tc = gather_gemm_tc_supported(cin, K, cout) && cin >= min_cin && ws && ws_bytes >= need;
+        // a shape the tensor-core kernel takes never drops to the SIMT kernel silently: a short workspace is an error
+        tc = gather_gemm_tc_supported(cin, K, cout);
+        CPD_REQUIRE(!tc || (ws && ws_bytes >= need), CPD_ERR_WORKSPACE, "cpd_gather_gemm: workspace too small (cpd_gather_gemm_workspace_bytes)");
     }
     if (tc) {
         uint8_t *p = reinterpret_cast<uint8_t *>(align_up((size_t)(uintptr_t)ws, 256));
@@ -410,36 +407,32 @@ extern "C" int32_t cpd_gather_wgrad(const float *x, const void *x_split, int64_t
     if (m_out == 0) return CPD_OK;
     const bool tap_major_ok = nbr_tap_major || K == 1;
     const size_t need = cpd_gather_wgrad_workspace_bytes(m_in, m_out, cin, K, cout, x_split != nullptr, dy_split != nullptr);
-    const bool rows_ok = gather_wgrad_rows_supported(cin, K, cout) && tap_major_ok && ws && ws_bytes >= need;
-    const bool pairs_ok = gather_wgrad_pairs_supported(cin, K, cout);
-    static const bool force_pairs = getenv("CPD_WGRAD_FORCE_PAIRS") != nullptr;                        // tuning knob
+    const bool shape_ok = gather_wgrad_rows_supported(cin, K, cout) && tap_major_ok;
     bool tc = false;
     if (algo == CPD_ALGO_TCGEN05) {
-        CPD_REQUIRE(rows_ok || pairs_ok, CPD_ERR_UNSUPPORTED, "cpd_gather_wgrad: tcgen05 path needs cin, cout >= 8 and multiples of 8 (and its workspace)");
+        CPD_REQUIRE(shape_ok, CPD_ERR_UNSUPPORTED, "cpd_gather_wgrad: tcgen05 path needs cin, cout >= 8 and multiples of 8 and the tap-major table");
         tc = true;
     } else if (algo == CPD_ALGO_AUTO) {
-        tc = rows_ok || pairs_ok;
+        tc = shape_ok;
     }
     if (tc) {
+        // never a silent drop to the SIMT kernel: a short workspace is an error
+        CPD_REQUIRE(ws && ws_bytes >= need, CPD_ERR_WORKSPACE, "cpd_gather_wgrad: workspace too small (cpd_gather_wgrad_workspace_bytes)");
         int32_t st;
-        if (rows_ok && !(force_pairs && pairs_ok)) {
-            uint8_t *p = reinterpret_cast<uint8_t *>(align_up((size_t)(uintptr_t)ws, 256));
-            const void *xs = x_split, *dys = dy_split;
-            if (!xs) {
-                st = split_rows(x, m_in, cin, p, nullptr, stream);
-                if (st) return st;
-                xs = p;
-                p += image_bytes(m_in, cin);
-            }
-            if (!dys) {
-                st = split_rows(dy, m_out, cout, p, nullptr, stream);
-                if (st) return st;
-                dys = p;
-            }
-            st = gather_wgrad_rows_tc(xs, cin, dys, m_out, cout, nbr, K, dw, stream);
-        } else {
-            st = gather_wgrad_pairs_tc(x, cin, dy, m_out, cout, nbr, K, nbr_tap_major, dw, stream);
+        uint8_t *p = reinterpret_cast<uint8_t *>(align_up((size_t)(uintptr_t)ws, 256));
+        const void *xs = x_split, *dys = dy_split;
+        if (!xs) {
+            st = split_rows(x, m_in, cin, p, nullptr, stream);
+            if (st) return st;
+            xs = p;
+            p += image_bytes(m_in, cin);
         }
+        if (!dys) {
+            st = split_rows(dy, m_out, cout, p, nullptr, stream);
+            if (st) return st;
+            dys = p;
+        }
+        st = gather_wgrad_rows_tc(xs, cin, dys, m_out, cout, nbr, K, dw, stream);
         if (st) return st;
     }
     const int co_tiles = (int)div_up(cout, 64), ci_tiles = (int)div_up(cin, 64);

@@ -98,6 +98,7 @@ struct TcArgs {
     float *stats, *y;
     long long m_out;
     int cin, K, cout, relu;
+    int cin_shift;              // log2(cin) when cin is a power of two (every CPD layer), else -1
 };
 
 // W (cout, Kf) fp32 -> pre-swizzled bf16 hi / lo tile images.  One thread per 16-byte output chunk.
@@ -302,7 +303,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
                 const int s = g % STAGES;
                 mbar_wait(empty0 + 8 * s, ((g / STAGES) & 1) ^ 1);
                 const int f = kb * BKE + c * 8;        // flattened (tap, channel) index of this thread's chunk
-                const int k = f / a.cin, ch = f - k * a.cin;
+                int k, ch;                              // (a runtime integer division here cost 12 % of the kernel's instructions)
+                if (a.cin_shift >= 0) { k = f >> a.cin_shift; ch = f & (a.cin - 1); }
+                else { k = f / a.cin; ch = f - k * a.cin; }
                 const bool k_ok = k < a.K;
                 const uint32_t dst = tiles_u32 + (uint32_t)(s * STAGE);
                 const uint8_t *col = a.xs + (size_t)ch * 2;
@@ -476,24 +479,16 @@ size_t smem_bytes(int K)
 
 int num_sms()
 {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
-    return n;
+    static PerDevice pd;
+    return device_sms(pd);
 }
 
 template <int BN>
 int32_t launch_tc(const TcArgs &a, cudaStream_t stream)
 {
     static_assert(stages_for(BN) * stage_bytes(BN) + 2 * MAX_TAPS * BM * 4 + 1024 + 256 <= 227 * 1024, "shared memory budget");
-    static bool configured = false;
-    if (!configured) {
-        CPD_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN>(MAX_TAPS)));
-        configured = true;
-    }
+    static PerDevice pd;
+    CPD_CUDA(opt_in_smem(pd, gather_gemm_tc_kernel<BN>, smem_bytes<BN>(MAX_TAPS)));
     const long long tiles = div_up(a.m_out, BM) * (a.cout / BN);
     const unsigned grid = (unsigned)(tiles < num_sms() ? tiles : num_sms());
     gather_gemm_tc_kernel<BN><<<grid, NTHREADS, smem_bytes<BN>(a.K), stream>>>(a);
@@ -558,7 +553,10 @@ int32_t gather_gemm_tc(const void *xs, int32_t cin, const float *w, int32_t K, i
     const long long chunks = (long long)n_kb * cout * 8;
     weight_split_kernel<<<(unsigned)div_up(chunks, 256), 256, 0, stream>>>(w, cout, Kf, n_kb, bn, wsplit, stats, tile_counter);
     count_launch();
-    TcArgs a{bias, scale, shift, residual, reinterpret_cast<const uint8_t *>(xs), wsplit, nbr, tile_counter, tile_masks, out_rows, stats, y, m_out, cin, K, cout, relu};
+    int cin_shift = -1;
+    if ((cin & (cin - 1)) == 0)
+        for (cin_shift = 0; (1 << cin_shift) < cin; ++cin_shift) {}
+    TcArgs a{bias, scale, shift, residual, reinterpret_cast<const uint8_t *>(xs), wsplit, nbr, tile_counter, tile_masks, out_rows, stats, y, m_out, cin, K, cout, relu, cin_shift};
     switch (cout) {
         case 16: return launch_tc<16>(a, stream);
         case 32: return launch_tc<32>(a, stream);

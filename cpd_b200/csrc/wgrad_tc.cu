@@ -350,11 +350,8 @@ template <int BN, int AM>
 int32_t launch_wg(const WgArgs &a, dim3 grid, cudaStream_t stream)
 {
     static_assert(wg_smem<BN, AM>() <= 227 * 1024, "shared memory budget");
-    static bool configured = false;
-    if (!configured) {
-        CPD_CUDA(cudaFuncSetAttribute(gather_wgrad_rows_kernel<BN, AM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem<BN, AM>()));
-        configured = true;
-    }
+    static PerDevice pd;
+    CPD_CUDA(opt_in_smem(pd, gather_wgrad_rows_kernel<BN, AM>, wg_smem<BN, AM>()));
     gather_wgrad_rows_kernel<BN, AM><<<grid, NTHREADS, wg_smem<BN, AM>(), stream>>>(a);
     count_launch();
     return launch_status("cpd_gather_wgrad[tcgen05]");

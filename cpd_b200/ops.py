@@ -125,7 +125,11 @@ def strided_outputs(coords, shape, batch, ksize, stride, padding):
         raise _lib.CpdError("cpd_rulebook_strided: empty output shape")
     ws = _ws(wsb, dev)
     oshape = (C.c_int32 * 3)()
-    cap = max(m * min(K, 8), 1)
+    # an input site feeds at most prod(ceil(k / s)) outputs (8 for the k=3, s=2 convs of the CPD towers, K for stride 1)
+    fan = 1
+    for k_, s_ in zip(ks, st):
+        fan *= -(-k_ // s_)
+    cap = max(m * min(K, fan), 1)
     ocoords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
     n_out = torch.empty((1,), dtype=torch.int32, device=dev)
     _lib.check(L.cpd_rulebook_strided_outputs(_ptr(coords), m, sh, int(batch), ks, st, pd, oshape, cap, _ptr(ocoords),
@@ -133,7 +137,10 @@ def strided_outputs(coords, shape, batch, ksize, stride, padding):
     mo = int(n_out.item())
     if mo > cap:
         raise _lib.CpdError("cpd_rulebook_strided_outputs: output capacity exceeded")
-    return ocoords[:mo], [int(oshape[0]), int(oshape[1]), int(oshape[2])]
+    out = ocoords[:mo]
+    if mo * 2 < cap:                 # do not pin the oversized buffer for the rulebook's lifetime
+        out = out.clone()
+    return out, [int(oshape[0]), int(oshape[1]), int(oshape[2])]
 
 
 def strided_tables(in_coords, in_shape, in_hash, out_coords, out_shape, out_hash, batch, ksize, stride, padding,

@@ -141,6 +141,7 @@ def torch_bev_reference(bb, head):
     """The reference's dense module structure in plain torch.nn (nn.Conv2d / nn.ConvTranspose2d /
     nn.BatchNorm2d, base_bev_backbone.py:31-59, center_head.py:11-45,73-94) sharing the mirrors' weights."""
     from cpd_b200 import bev
+    pairs = []                     # (mirror module, plain torch module) for every parametrised layer
 
     def seq(ds):
         layers = []
@@ -153,14 +154,17 @@ def torch_bev_reference(bb, head):
                 if m.bias is not None:
                     c.bias.data.copy_(m.bias.data)
                 layers.append(c)
+                pairs.append((m, c))
             elif isinstance(m, bev.DenseConvTranspose2d):
                 c = nn.ConvTranspose2d(m.in_channels, m.out_channels, m.s, stride=m.s, bias=False)
                 c.weight.data.copy_(m.weight.data)
                 layers.append(c)
+                pairs.append((m, c))
             elif isinstance(m, nn.BatchNorm2d):
                 b = nn.BatchNorm2d(m.num_features, eps=m.eps, momentum=m.momentum)
                 b.load_state_dict(m.state_dict())
                 layers.append(b)
+                pairs.append((m, b))
             elif isinstance(m, nn.ReLU):
                 layers.append(nn.ReLU())
             else:
@@ -179,6 +183,7 @@ def torch_bev_reference(bb, head):
         s = shared(f)
         return f, [{n: m(s) for n, m in hd.items()} for hd in heads]
     mods = nn.ModuleList(blocks + deblocks + [shared] + [m for hd in heads for m in hd.values()])
+    run.pairs = pairs
     return run, mods
 
 
@@ -190,6 +195,7 @@ class CpuDetector:
         self.det = copy.deepcopy(det).cpu().train()
         self.run_dense, self.dense_mods = torch_bev_reference(self.det.backbone_2d, self.det.dense_head)
         self.dense_mods.train()
+        self.opt = None
 
     def _tower(self, sfx, frames, names):
         det = self.det
@@ -206,7 +212,8 @@ class CpuDetector:
             outs.append(f)
         return f, co, shape, outs
 
-    def train_step(self, frames, frames1, gt_boxes):
+    def train_step(self, frames, frames1, gt_boxes, optimizer=False):
+        """forward + backward (+ grad-clip + Adam update with optimizer=True, as bench.py's CUDA arm does)."""
         from cpd_b200 import bev
         det = self.det
         f, co, shape, _ = self._tower("", frames, ["conv_input", "conv1", "conv2", "conv3", "conv4", "conv_out"])
@@ -227,4 +234,24 @@ class CpuDetector:
         for p in params:
             p.grad = None
         loss.backward()
+        if optimizer:
+            live = [p for p in params if p.grad is not None]
+            if self.opt is None:
+                self.opt = torch.optim.Adam(live, lr=1e-4)
+            torch.nn.utils.clip_grad_norm_(live, 10.0)
+            self.opt.step()
         return float(loss)
+
+    def named_grads(self):
+        """Gradients of the last train_step keyed by the parameter names of CPDHotPathDetector (the dense layers'
+        gradients live on their plain-torch twins)."""
+        twin = {}
+        for mirror, ref in self.run_dense.pairs:
+            for n, p in mirror.named_parameters(recurse=False):
+                twin[id(p)] = getattr(ref, n)
+        out = {}
+        for name, p in self.det.named_parameters():
+            q = twin.get(id(p), p)
+            if q.grad is not None:
+                out[name] = q.grad.detach().clone()
+        return out
