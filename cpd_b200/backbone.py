@@ -151,9 +151,14 @@ class _Backbone8xBase(nn.Module):
                     rb, out_hash = m.get_rulebook(x)
                     if rb.nbr_fwd.shape[1] > 1:
                         rb.nbr_fwd_t                  # transposed table for the weight-gradient kernel
-                    rb.masks_fwd                      # per-tile tap masks (k-block skipping)
-                    if rb.kind == "strided" and self.training:
-                        rb.bwd_sorted()               # input-gradient table grouped by tap pattern
+                    cin = m.in_channels + (-m.in_channels) % 8
+                    if rb.sorted_table("fwd", cin) is None:
+                        rb.masks_fwd                  # per-tile tap masks (k-block skipping) of the unsorted table
+                    if self.training and torch.is_grad_enabled():
+                        if rb.kind == "strided":
+                            rb.bwd_sorted(m.out_channels)                 # input-gradient table in tap-pattern order
+                        elif cin == m.in_channels:                        # (the 5-channel input needs no gradient)
+                            rb.sorted_table("fwd", m.out_channels)
                     x = m._wrap_output(x, rb, out_hash, None)
         return dict(perm=perm, coords=coords, indice_dict=x.indice_dict)
 

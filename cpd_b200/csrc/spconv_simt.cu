@@ -12,6 +12,7 @@ namespace cpd {
 
 int32_t split_rows(const float *x, int64_t m, int32_t c, void *xs, float *colsum, cudaStream_t stream);
 int32_t tile_tap_masks(const int32_t *nbr, int64_t m, int32_t K, uint32_t *masks, cudaStream_t stream);
+int32_t tap_block_keys(const int32_t *nbr, int64_t m, int32_t K, int32_t tpb, int32_t *keys, cudaStream_t stream);
 int32_t gather_gemm_tc(const void *xs, int32_t cin, const float *w, int32_t K, int32_t cout,
                        const int32_t *nbr, const uint32_t *tile_masks, const int32_t *out_rows, int64_t m_out, const float *bias, const float *scale, const float *shift,
                        const float *residual, int32_t relu, float *stats, float *y, void *ws, size_t ws_bytes,
@@ -340,6 +341,12 @@ extern "C" int32_t cpd_tile_tap_masks(const int32_t *nbr, int64_t m, int32_t K, 
 {
     CPD_REQUIRE(nbr && masks && m >= 0, CPD_ERR_BAD_ARG, "cpd_tile_tap_masks: bad argument");
     return tile_tap_masks(nbr, m, K, masks, (cudaStream_t)stream);
+}
+
+extern "C" int32_t cpd_tap_block_keys(const int32_t *nbr, int64_t m, int32_t K, int32_t taps_per_block, int32_t *keys, cpd_stream_t stream)
+{
+    CPD_REQUIRE(nbr && keys && m >= 0, CPD_ERR_BAD_ARG, "cpd_tap_block_keys: bad argument");
+    return tap_block_keys(nbr, m, K, taps_per_block, keys, (cudaStream_t)stream);
 }
 
 extern "C" int32_t cpd_gather_gemm(const float *x, const void *x_split, int64_t m_in, int32_t cin, const float *w, int32_t K,

@@ -530,6 +530,28 @@ __global__ void tile_masks_kernel(const int32_t *__restrict__ nbr, long long m, 
     if (threadIdx.x == 0) masks[blockIdx.x] = acc;
 }
 
+// Sort key of a table row = bitmap of the k-blocks it needs: bit j set iff the row has a neighbour at any of the taps
+// [j * tpb, (j + 1) * tpb).  Rows with equal keys keep each other's k-blocks busy: visiting the table in key order
+// (Rulebook.sorted_table) makes every 128-row tile skip the k-blocks none of its rows needs.
+__global__ void tap_block_keys_kernel(const int32_t *__restrict__ nbr, long long m, int K, int tpb, int32_t *__restrict__ keys)
+{
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= m) return;
+    uint32_t key = 0u;
+    for (int k = 0; k < K; ++k)
+        if (__ldg(nbr + row * K + k) >= 0) key |= 1u << (k / tpb);
+    keys[row] = (int32_t)key;
+}
+
+int32_t tap_block_keys(const int32_t *nbr, int64_t m, int32_t K, int32_t tpb, int32_t *keys, cudaStream_t stream)
+{
+    CPD_REQUIRE(K >= 1 && tpb >= 1 && (K + tpb - 1) / tpb <= 31, CPD_ERR_UNSUPPORTED, "cpd_tap_block_keys: at most 31 tap blocks");
+    if (m == 0) return CPD_OK;
+    tap_block_keys_kernel<<<(unsigned)div_up(m, 256), 256, 0, stream>>>(nbr, m, K, tpb, keys);
+    count_launch();
+    return launch_status("cpd_tap_block_keys");
+}
+
 int32_t tile_tap_masks(const int32_t *nbr, int64_t m, int32_t K, uint32_t *masks, cudaStream_t stream)
 {
     CPD_REQUIRE(K >= 1 && K <= 32, CPD_ERR_UNSUPPORTED, "cpd_tile_tap_masks: at most 32 taps");

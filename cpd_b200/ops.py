@@ -215,6 +215,17 @@ def tile_tap_masks(nbr):
     return masks
 
 
+def tap_block_keys(nbr, taps_per_block):
+    """Per table row: bitmap of the k-blocks (groups of taps_per_block taps) it has neighbours in -- the sort key of
+    Rulebook.sorted_table."""
+    _need_cuda(nbr)
+    L = _lib.lib()
+    m, K = nbr.shape
+    keys = torch.empty((m,), dtype=torch.int32, device=nbr.device)
+    _lib.check(L.cpd_tap_block_keys(_ptr(nbr), m, K, int(taps_per_block), _ptr(keys), _stream()), "cpd_tap_block_keys")
+    return keys
+
+
 def gather_gemm(x, w, nbr, bias=None, scale=None, shift=None, residual=None, relu=False, stats=None,
                 algo=ALGO_AUTO, out=None, x_split=None, tile_masks=None, out_rows=None):
     """y[o] = epi(sum_k W[:,k,:] x[nbr[o,k]]);  w is (cout, K, cin) (any (cout, ..., cin) view).

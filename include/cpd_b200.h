@@ -142,6 +142,13 @@ CPD_API int32_t cpd_split_rows(const float *x, int64_t m, int32_t c, void *xs, f
  * table) and passed to cpd_gather_gemm, whose tensor-core kernel then skips the k-blocks of absent taps. */
 CPD_API int32_t cpd_tile_tap_masks(const int32_t *nbr, int64_t m, int32_t K, uint32_t *masks, cpd_stream_t stream);
 
+/* Row sort key for visiting a neighbour table in tap-pattern order: keys[row] bit j = the row has a neighbour at one of the taps
+ * [j * taps_per_block, (j + 1) * taps_per_block) -- i.e. the k-blocks of the tensor-core kernel the row needs
+ * (taps_per_block = 64 / cin for cin < 64, else 1).  Rows sorted by key share their k-blocks, so a 128-row tile of the
+ * sorted table skips (through cpd_tile_tap_masks) every k-block none of its rows uses; results go back to their rows
+ * through cpd_gather_gemm's out_rows.  ceil(K / taps_per_block) <= 31. */
+CPD_API int32_t cpd_tap_block_keys(const int32_t *nbr, int64_t m, int32_t K, int32_t taps_per_block, int32_t *keys, cpd_stream_t stream);
+
 /* x_split (NULL ok): split-row image of x (cpd_split_rows); have_x_split tells the workspace query
  * whether the call will pass one.  tile_masks (NULL ok): cpd_tile_tap_masks(nbr).
  * out_rows (NULL ok, tensor-core kernel only): a permutation of [0, m_out); row r of the table is written to

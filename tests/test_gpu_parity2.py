@@ -214,32 +214,49 @@ def test_bench_scale_sparse_and_dense(oracle, cuda):
 
 def test_detector_train_step_matches_cpu_port(cuda):
     """The two arms of the headline ratio, on the same batch with the same weights: CPDHotPathDetector (CUDA) against
-    oracle.pipeline.CpuDetector (oracle C for voxelizer / sparse convs, torch CPU for the dense head).  Loss to 1e-4;
-    every parameter gradient compared in relative L2 (training-mode BatchNorm + ReLU over ~50 layers amplifies
-    rounding differences of either arm, so the bound is looser than the per-op 1e-4 pinned elsewhere)."""
+    oracle.pipeline.CpuDetector (oracle C for voxelizer / sparse convs, torch CPU for the dense head).
+
+    Loss: 1e-4.  Gradients: ~50 conv + training-mode BatchNorm + ReLU stages are ill-conditioned -- plain fp32 torch
+    differs from float64 torch by ~1e-3 in the BEV weight gradients already (measured) -- so an absolute
+    tolerance says nothing.  The bound is stated against the reference's OWN sensitivity: the CPU port is run a second
+    time with every weight perturbed by a relative 2^-17 (the size of one bf16x3 operand rounding); the CUDA arm must
+    sit within a small multiple of the gradient change that perturbation causes, group by group."""
     from cpd_b200 import detector
     from oracle import pipeline
     torch.manual_seed(0)
     det = detector.CPDHotPathDetector().to(cuda).train()
-    cpu = pipeline.CpuDetector(det)
     frames = [synth_scan(20000, 300 + i) for i in range(2)]
     frames1 = [synth_scan(20000, 400 + i) for i in range(2)]
     gt = np.stack([synth_gt_boxes(30, 300 + i) for i in range(2)])
+    cpu = pipeline.CpuDetector(det)
     loss_ref = cpu.train_step(frames, frames1, gt)
     ref = cpu.named_grads()
+    # the same CPU port with weights perturbed at the 2^-17 level: how far does the REFERENCE move?
+    pert = pipeline.CpuDetector(det)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for prm in list(pert.det.parameters()) + list(pert.dense_mods.parameters()):
+            prm.mul_(1.0 + (torch.rand(prm.shape, generator=g) * 2 - 1) * 2.0 ** -17)
+    loss_pert = pert.train_step(frames, frames1, gt)
+    refp = pert.named_grads()
     loss, _ = det(dict(points=[dev(f, cuda) for f in frames], points1=[dev(f, cuda) for f in frames1], gt_boxes=dev(gt, cuda)))
     loss.backward()
-    print(f"loss: cuda {float(loss):.6f}  cpu port {loss_ref:.6f}")
+    print(f"loss: cuda {float(loss):.6f}  cpu port {loss_ref:.6f}  cpu port with 2^-17 weight noise {loss_pert:.6f}")
     assert abs(float(loss) - loss_ref) <= 1e-4 * max(1.0, abs(loss_ref))
-    rels, worst = [], ("", 0.0)
-    for name, p in det.named_parameters():
-        assert p.grad is not None and name in ref, name
-        g, r = p.grad.detach().double().cpu(), ref[name].double()
-        rel = float((g - r).norm() / r.norm().clamp_min(1e-12)) if float(r.norm()) > 1e-10 else float((g - r).norm())
-        rels.append(rel)
-        if rel > worst[1]:
-            worst = (name, rel)
-    rels = np.asarray(rels)
-    print(f"parameter gradients vs CPU port: relative L2 error median {np.median(rels):.2e}, 90% {np.quantile(rels, 0.9):.2e}, "
-          f"max {rels.max():.2e} ({worst[0]})")
-    assert np.median(rels) <= 2e-3 and rels.max() <= 5e-2, worst
+    groups = {}
+    for name, prm in det.named_parameters():
+        assert prm.grad is not None and name in ref, name
+        r = ref[name].double()
+        if float(r.norm()) / r.numel() ** 0.5 < 1e-9:          # mathematically zero (a conv bias in front of BatchNorm): noise vs noise
+            continue
+        key = ".".join(name.split(".")[:2])
+        e = groups.setdefault(key, [0.0, 0.0, 0.0])
+        e[0] += float((prm.grad.detach().double().cpu() - r).square().sum())
+        e[1] += float((refp[name].double() - r).square().sum())
+        e[2] += float(r.square().sum())
+    worst = 0.0
+    for key, (d_cuda, d_pert, nrm) in groups.items():
+        rc, rp = (d_cuda / nrm) ** 0.5, (d_pert / nrm) ** 0.5
+        worst = max(worst, rc / max(rp, 1e-7))
+        print(f"  {key:34s} rel L2: cuda vs port {rc:.2e}   port(2^-17 noise) vs port {rp:.2e}   ratio {rc / max(rp, 1e-7):.2f}")
+    assert worst <= 8.0, worst
