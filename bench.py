@@ -273,10 +273,13 @@ def run_ours(a):
     groups, pcache = {}, {}
     for e0, e1, m in prof:
         key = (m["kind"], m["cin"], m["cout"], m["K"])
-        nid = id(m["nbr"])
-        if nid not in pcache:
-            pcache[nid] = int((m["nbr"] >= 0).sum().item())
-        P = pcache[nid]
+        if "P" in m:                                     # dense TMA convs: every tap of every output pixel
+            P = m["P"]
+        else:
+            nid = id(m["nbr"])
+            if nid not in pcache:
+                pcache[nid] = int((m["nbr"] >= 0).sum().item())
+            P = pcache[nid]
         g = groups.setdefault(key, dict(ms=0.0, n=0, bytes=0.0, flops=0.0))
         g["ms"] += e0.elapsed_time(e1); g["n"] += 1
         g["bytes"] += 4.0 * (m["m_in"] * m["cin"] + m["m_out"] * m["cout"]) + 8.0 * P + 4.0 * m["K"] * m["cin"] * m["cout"]

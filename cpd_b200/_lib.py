@@ -34,6 +34,15 @@ SIGNATURES = {
     "cpd_bn_train_bwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "cpd_weight_transpose": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "cpd_conv2d_table": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "cpd_conv2d_supported": (_i32, [_i32, _i32, _i32, _i32]),
+    "cpd_conv2d_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "cpd_conv2d_fwd": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "cpd_conv2d_dgrad_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "cpd_conv2d_dgrad": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "cpd_conv2d_wgrad_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32]),
+    "cpd_conv2d_wgrad": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "cpd_convt2d_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "cpd_convt2d_fwd": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "cpd_sparse_to_dense": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp]),
     "cpd_sparse_to_dense_bwd": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp]),
     "cpd_overlap_bev": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp]),

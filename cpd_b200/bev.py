@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 from . import iou3d_nms_utils, ops
 from .backbone import _cfg
-from .sparse import Rulebook, _GatherConv, bn_fusable, bn_train, fold_bn
+from .sparse import Rulebook, _GatherConv, _carried_split, bn_fusable, bn_train, fold_bn
 
 
 class DenseMap:
@@ -57,6 +57,8 @@ def pixel_tables(n, h, w, kh, kw, stride, pad, device):
             fwd = ops.conv2d_table(n, h, w, kh, kw, stride, pad, False, ho, wo, device)
             bwd = ops.conv2d_table(n, ho, wo, kh, kw, stride, pad, True, h, w, device)
         rb = Rulebook("strided", fwd, bwd, None, None, None, None, [1, kh, kw], [1, stride, stride], [0, pad, pad])
+        if kh == kw:                                     # geometry for the table-free TMA kernel (cpd_conv2d_fwd / _dgrad)
+            rb.geo = dict(n=n, h=h, w=w, k=kh, stride=stride, pad=pad, ho=ho, wo=wo)
         _TABLES[key] = (rb, ho, wo)
     return _TABLES[key]
 
@@ -83,8 +85,12 @@ class DenseConv2d(nn.Module):
     def forward(self, x, scale=None, shift=None, relu=False):
         rb, ho, wo = pixel_tables(x.n, x.h, x.w, self.k, self.k, self.stride, self.padding, x.data.device)
         if scale is not None or relu:   # inference: folded BatchNorm (+ReLU) in the epilogue
-            y = ops.gather_gemm(x.data, self.w_kc().contiguous(), rb.nbr_fwd, bias=self.bias, scale=scale, shift=shift,
-                                relu=relu, algo=self.algo)
+            if self.stride == 1 and self.algo != ops.ALGO_SIMT and ops.conv2d_ok(self.in_channels, self.k, self.out_channels):
+                y = ops.conv2d_fwd(ops.split_rows(x.data), x.n, x.h, x.w, self.w_kc().contiguous(), self.k, self.padding, bias=self.bias,
+                                   scale=scale, shift=shift, relu=relu)
+            else:
+                y = ops.gather_gemm(x.data, self.w_kc().contiguous(), rb.nbr_fwd, bias=self.bias, scale=scale, shift=shift,
+                                    relu=relu, algo=self.algo)
         else:
             y = _GatherConv.apply(x.data, self.w_kc().contiguous(), self.bias, rb, self.algo)
         return DenseMap(y, x.n, ho, wo)
@@ -94,6 +100,49 @@ class DenseConv2d(nn.Module):
         rb, ho, wo = pixel_tables(x.n, x.h, x.w, self.k, self.k, self.stride, self.padding, x.data.device)
         y, stats = _GatherConv.apply(x.data, self.w_kc().contiguous(), self.bias, rb, self.algo, True)
         return DenseMap(bn_train(y, stats, bn, relu, dx_split=self.bias is None), x.n, ho, wo)
+
+
+class _ConvT2d(torch.autograd.Function):
+    """nn.ConvTranspose2d with kernel == stride == s > 1 on row matrices.  Forward: s*s 1x1 GEMMs whose epilogues write the
+    pixel-shuffled map directly (cpd_convt2d_fwd).  Backward: ONE pixel-unshuffle copy of dy to (m, s*s*cout) rows, then the
+    input-gradient is a single 1x1 GEMM over s*s*cout channels and the weight-gradient a single K = 1 reduction."""
+
+    @staticmethod
+    def forward(ctx, x, weight, n, h, w, want_stats):
+        s = weight.shape[2]
+        xs = _carried_split(x)
+        if xs is None:
+            xs = ops.split_rows(x)
+        stats = torch.empty((2, weight.shape[1]), dtype=torch.float32, device=x.device) if want_stats else None
+        y = ops.convt2d_fwd(xs, n, h, w, weight, s, stats=stats)
+        ctx.save_for_backward(x, weight)
+        ctx.xs, ctx.geo = xs, (n, h, w, s)
+        if not want_stats:
+            return y
+        ctx.mark_non_differentiable(stats)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, *unused):
+        x, weight = ctx.saved_tensors
+        n, h, w, s = ctx.geo
+        cin, cout = weight.shape[0], weight.shape[1]
+        m = n * h * w
+        dy = dy.contiguous()
+        # (n, h, s, w, s, cout) -> (n, h, w, s, s, cout): row p holds the s*s output pixels input pixel p feeds
+        dy4 = dy.view(n, h, s, w, s, cout).permute(0, 1, 3, 2, 4, 5).reshape(m, s * s * cout)
+        dys = ops.split_rows(dy4)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            # dx[p, ci] = sum_{k, co} dy4[p, (k, co)] W[ci, co, k]: a 1x1 conv with weight (cin, 1, s*s*cout)
+            wd = weight.permute(0, 2, 3, 1).reshape(cin, 1, s * s * cout).contiguous()
+            dx = ops.conv2d_fwd(dys, n, h, w, wd, 1, 0)
+        if ctx.needs_input_grad[1]:
+            ident = pixel_tables(n, h, w, 1, 1, 1, 0, x.device)[0].nbr_fwd
+            dwk, _ = ops.gather_wgrad(x, dy4, ident, x_split=ctx.xs, dy_split=dys)          # (s*s*cout, 1, cin)
+            dw = dwk.view(s, s, cout, cin).permute(3, 2, 0, 1).contiguous()
+        ctx.xs = None
+        return dx, dw, None, None, None, None
 
 
 class DenseConvTranspose2d(nn.Module):
@@ -109,15 +158,26 @@ class DenseConvTranspose2d(nn.Module):
         nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
         self.bias = None
 
+    def _tma(self):
+        return self.algo != ops.ALGO_SIMT and ops.conv2d_ok(self.in_channels, 1, self.out_channels) and \
+            ops.conv2d_ok(self.s * self.s * self.out_channels, 1, self.in_channels)
+
     def forward(self, x, scale=None, shift=None, relu=False):
         s = self.s
         rb, _, _ = pixel_tables(x.n, x.h, x.w, 1, 1, 1, 0, x.data.device)
         fused = scale is not None or relu
         if s == 1:
             w = self.weight[:, :, 0, 0].t().reshape(self.out_channels, 1, self.in_channels).contiguous()
-            y = (ops.gather_gemm(x.data, w, rb.nbr_fwd, scale=scale, shift=shift, relu=relu, algo=self.algo) if fused
-                 else _GatherConv.apply(x.data, w, None, rb, self.algo))
+            if fused and self._tma():
+                y = ops.conv2d_fwd(ops.split_rows(x.data), x.n, x.h, x.w, w, 1, 0, scale=scale, shift=shift, relu=relu)
+            else:
+                y = (ops.gather_gemm(x.data, w, rb.nbr_fwd, scale=scale, shift=shift, relu=relu, algo=self.algo) if fused
+                     else _GatherConv.apply(x.data, w, None, rb, self.algo))
             return DenseMap(y, x.n, x.h, x.w)
+        if self._tma():
+            y = (ops.convt2d_fwd(ops.split_rows(x.data), x.n, x.h, x.w, self.weight, s, scale=scale, shift=shift, relu=relu) if fused
+                 else _ConvT2d.apply(x.data, self.weight, x.n, x.h, x.w, False))
+            return DenseMap(y, x.n, x.h * s, x.w * s)
         out = x.data.new_empty((x.n, x.h * s, x.w * s, self.out_channels))
         for ky in range(s):
             for kx in range(s):
@@ -126,6 +186,17 @@ class DenseConvTranspose2d(nn.Module):
                      else _GatherConv.apply(x.data, w, None, rb, self.algo))
                 out[:, ky::s, kx::s, :] = y.view(x.n, x.h, x.w, self.out_channels)
         return DenseMap(out.view(-1, self.out_channels), x.n, x.h * s, x.w * s)
+
+    def forward_bn_train(self, x, bn, relu):
+        """Training: the GEMM epilogues emit the batch statistics of the whole output map, then one fused normalise(+ReLU) pass."""
+        s = self.s
+        if s == 1:
+            rb, _, _ = pixel_tables(x.n, x.h, x.w, 1, 1, 1, 0, x.data.device)
+            w = self.weight[:, :, 0, 0].t().reshape(self.out_channels, 1, self.in_channels).contiguous()
+            y, stats = _GatherConv.apply(x.data, w, None, rb, self.algo, True)
+        else:
+            y, stats = _ConvT2d.apply(x.data, self.weight, x.n, x.h, x.w, True)
+        return DenseMap(bn_train(y, stats, bn, relu, dx_split=s == 1), x.n, x.h * s, x.w * s)
 
 
 class DenseSequential(nn.Sequential):
@@ -147,7 +218,7 @@ class DenseSequential(nn.Sequential):
                     x = m(x, scale=sc, shift=sh, relu=has_relu)
                     i += 1 + (bn is not None) + has_relu
                     continue
-                if isinstance(m, DenseConv2d) and bn is not None and bn_fusable(bn):
+                if bn is not None and bn_fusable(bn) and (isinstance(m, DenseConv2d) or m.s == 1 or m._tma()):
                     x = m.forward_bn_train(x, bn, has_relu)
                     i += 2 + has_relu
                     continue

@@ -47,6 +47,8 @@
 // layer outputs, tools/tc_check.py) and moves half the shared-memory bytes of a 3xTF32 split --
 // and shared-memory bandwidth (operand stores + UMMA operand reads), not the tensor pipe, is what
 // bounds a 3-product emulation at M = N = 128.
+#include <cuda.h>
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace cpd {
@@ -57,15 +59,14 @@ constexpr int BM = 128;       // UMMA M
 constexpr int BKE = 64;       // bf16 elements per k-block = 128 bytes = one swizzle row
 constexpr int NEPI = 128;     // warps 0-3: epilogue (TMEM lane quarter = warp index)
 constexpr int NPW = 8;        // warps 4-11: producers
-constexpr int NPROD = NPW * 32;
-constexpr int MMA_WARP = (NEPI + NPROD) / 32;      // warp 12: MMA issuer, warp 13: loader
-constexpr int NTHREADS = NEPI + NPROD + 64;
-constexpr int RSTEP = NPROD / 8;   // row stride between the chunks one producer thread owns (8 x 16 B chunks per row)
+constexpr int NPROD_SP = NPW * 32;                 // sparse kernel: warp 12 = MMA issuer, warp 13 = loader
+constexpr int NTHREADS_SP = NEPI + NPROD_SP + 64;
+constexpr int NTHREADS_DENSE = NEPI + 64;          // dense kernel: no producers; warp 4 = MMA issuer, warp 5 = loader
+constexpr int RSTEP = NPROD_SP / 8;   // row stride between the chunks one producer thread owns (8 x 16 B chunks per row)
 constexpr int A_V = BM / RSTEP;    // rows per producer thread per k-block
 constexpr int MAX_TAPS = 27;
 constexpr int SCHED_R = 4;                     // depth of the tile-id ring
 constexpr int KBW = 4;                         // 32-bit words of the per-tile active-k-block bitmap (n_kb <= 128)
-constexpr int NCONS = NTHREADS / 32;           // every warp consumes the tile sequence
 
 __host__ __device__ constexpr int stage_bytes(int bn) { return 2 * BM * 128 + 2 * bn * 128; }
 __host__ __device__ constexpr int stages_for(int bn) { return bn >= 256 ? 2 : bn >= 128 ? 3 : bn >= 32 ? 4 : 5; }
@@ -99,6 +100,22 @@ struct TcArgs {
     long long m_out;
     int cin, K, cout, relu;
     int cin_shift;              // log2(cin) when cin is a power of two (every CPD layer), else -1
+};
+
+// DENSE variant (cpd_conv2d_fwd / cpd_conv2d_dgrad: the dense BEV convolutions, stride 1): the rows of an output tile are a
+// DT_W x DT_H pixel patch of one image and the A operand of tap (ky, kx), channel block cb is the SAME patch shifted by
+// (ky - pad, kx - pad) -- a 4-D box {64 channels, DT_W, DT_H, 1} of the NHWC split-row image that ONE tiled TMA load
+// (cp.async.bulk.tensor.4d, tensor map over [2 C, W, H, N]) lands in the K-major SWIZZLE_128B layout, zero-filling the
+// conv padding and the ragged image border by itself.  No neighbour table, no producer warps, no LSU work.
+constexpr int DT_W = 16, DT_H = 8;          // 128 pixels per tile
+static_assert(DT_W * DT_H == BM, "dense tile = one UMMA M");
+struct DenseGeo {
+    int n, h, w;                // input image batch (NHWC rows)
+    int ho, wo;                 // conv output size: h + 2 pad - kh + 1, w + 2 pad - kw + 1
+    int kh, kw, pad;
+    int tiles_x, tiles_y;
+    int out_h, out_w, out_sy, out_sx, out_oy, out_ox;   // output pixel (y, x) is written to (y * out_sy + out_oy, x * out_sx + out_ox) of an
+                                                        // (n, out_h, out_w) map: (ho, wo, 1, 1, 0, 0) for a conv, the pixel shuffle of ConvTranspose k == s
 };
 
 // W (cout, Kf) fp32 -> pre-swizzled bf16 hi / lo tile images.  One thread per 16-byte output chunk.
@@ -143,9 +160,11 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&x)[32], int lane)
     return x[0];
 }
 
-template <int BN>
-__global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
+template <int BN, bool DENSE>
+__global__ void __launch_bounds__(DENSE ? NTHREADS_DENSE : NTHREADS_SP, 1) gather_gemm_tc_kernel(TcArgs a, const __grid_constant__ CUtensorMap xmap, DenseGeo dg)
 {
+    // warp roles: epilogue 0-3 | producers (sparse only) | MMA | loader
+    constexpr int NPROD = DENSE ? 0 : NPROD_SP, MMA_WARP = (NEPI + NPROD) / 32, NCONS = (NEPI + NPROD + 64) / 32;   // every warp consumes the tile sequence
     constexpr int STAGES = stages_for(BN), ACC = acc_bufs(BN);
     constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE = stage_bytes(BN);
     // fp32 accumulate (bit 4), bf16 A and B (bits 7, 10), K-major both, N >> 3, M >> 4
@@ -153,7 +172,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int tbl_ints = BM * a.K;
+    const int tbl_ints = DENSE ? 0 : BM * a.K;
     int32_t *nbr_s = reinterpret_cast<int32_t *>(tiles + STAGES * STAGE);          // [2][BM][K]
     uint64_t *bars = reinterpret_cast<uint64_t *>(nbr_s + 2 * tbl_ints);          // full[S] empty[S] tbl_full[2] tbl_empty[2] acc_full[2] acc_empty[2]
     uint32_t *misc = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 8 + 2 * SCHED_R);   // [0] tmem base, [4..) tile ring
@@ -165,8 +184,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Kf = a.K * a.cin;
     const int n_kb = (Kf + BKE - 1) / BKE;
-    const int ntn = a.cout / BN;                                   // cout tiles (cout > 256 only)
-    const long long total_tiles = ((a.m_out + BM - 1) / BM) * ntn;
+    const int ntn = a.cout / BN;                                   // cout tiles
+    const long long total_tiles = (DENSE ? (long long)dg.n * dg.tiles_y * dg.tiles_x : (a.m_out + BM - 1) / BM) * ntn;
 
     if (warp == MMA_WARP) {
         if (lane == 0) {
@@ -219,10 +238,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
             const int buf = ACC == 2 ? (ti & 1) : 0;
             mbar_wait(accf0 + 8 * buf, ACC == 2 ? ((ti >> 1) & 1) : (ti & 1));
             tc_fence_after();
-            const long long trow = (t / ntn) * BM + warp * 32 + lane;      // row of the table / tile
             const int n0 = (int)(t % ntn) * BN;
-            const bool valid = trow < a.m_out;
-            const long long row = (valid && a.out_rows) ? (long long)__ldg(a.out_rows + trow) : trow;   // row of y (and of the residual)
+            bool valid;
+            long long row;                                                 // row of y (and of the residual)
+            if (DENSE) {
+                const int pt = (int)(t / ntn), r = warp * 32 + lane;       // pixel tile, pixel inside it (x fastest)
+                const int img = pt / (dg.tiles_x * dg.tiles_y), rem = pt - img * (dg.tiles_x * dg.tiles_y);
+                const int y = (rem / dg.tiles_x) * DT_H + r / DT_W, x = (rem % dg.tiles_x) * DT_W + r % DT_W;
+                valid = y < dg.ho && x < dg.wo;
+                row = ((long long)img * dg.out_h + (y * dg.out_sy + dg.out_oy)) * dg.out_w + (x * dg.out_sx + dg.out_ox);
+            } else {
+                const long long trow = (t / ntn) * BM + warp * 32 + lane;  // row of the table / tile
+                valid = trow < a.m_out;
+                row = (valid && a.out_rows) ? (long long)__ldg(a.out_rows + trow) : trow;
+            }
             const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 2 * BN);
 #pragma unroll
             for (int i = 0; i < BN / 16; ++i) {
@@ -281,8 +310,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
 #pragma unroll
             for (int i = 0; i < BN / 16; ++i) atomicAdd(a.stats + (lane < 16 ? 0 : a.cout) + 16 * i + (lane & 15), st_acc[i]);
         }
-    } else if (warp < MMA_WARP) {
-        // ================= producers (warps 4-11) =================
+    } else if (!DENSE && warp < MMA_WARP) {
+        // ================= producers (warps 4-11; sparse kernel only) =================
         const int ptid = tid - NEPI;
         const int c = ptid & 7, r_base = ptid >> 3;   // 16-byte smem chunk (8 channels), first row (rows r_base + RSTEP j)
         uint32_t soff[A_V];                           // swizzled byte offsets of this thread's chunks (loop invariant)
@@ -433,29 +462,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_gemm_tc_kernel(TcArgs a)
             }
             __syncwarp();
         };
+        if (DENSE && lane == 0) tma_prefetch_desc(&xmap);
         publish(0);
         long long t = fetch_tile(0);
-        if (t < total_tiles) load_table(t, 0);
+        if (!DENSE && t < total_tiles) load_table(t, 0);
+        const int cpb = a.cin / BKE;                                   // DENSE: 64-channel blocks per tap (cin % 64 == 0)
         int g = 0, ti = 0;
         for (; t < total_tiles; ++ti) {
             const uint32_t c0 = km0, c1 = km1, c2 = km2, c3 = km3;     // this tile's k-block map (fetch_tile overwrites km*)
             auto kb_active_cur = [&](int kb) -> bool { return kb_bit(kb, c0, c1, c2, c3); };
             publish(ti + 1);
             const long long t_next = fetch_tile(ti + 1);
-            if (t_next < total_tiles) {
+            if (!DENSE && t_next < total_tiles) {
                 const int tbn = (ti + 1) & 1;
                 mbar_wait(tble0 + 8 * tbn, (((ti + 1) >> 1) & 1) ^ 1);             // producers are done with the tile that used this buffer
                 load_table(t_next, tbn);
             }
             const int nt = (int)(t % ntn);
+            int img = 0, x0 = 0, y0 = 0;                               // DENSE: origin of the tile's pixel patch
+            if (DENSE) {
+                const int pt = (int)(t / ntn);
+                img = pt / (dg.tiles_x * dg.tiles_y);
+                const int rem = pt - img * (dg.tiles_x * dg.tiles_y);
+                y0 = (rem / dg.tiles_x) * DT_H - dg.pad; x0 = (rem % dg.tiles_x) * DT_W - dg.pad;
+            }
             for (int kb = 0; kb < n_kb; ++kb) {
                 if (!kb_active_cur(kb)) continue;
                 const int s = g % STAGES;
                 if (lane == 0) {
                     mbar_wait(empty0 + 8 * s, ((g / STAGES) & 1) ^ 1);
                     const uint8_t *src = a.wsplit + ((size_t)kb * ntn + nt) * (size_t)tile_bytes;
-                    mbar_arrive_expect_tx(full0 + 8 * s, tile_bytes);
-                    bulk_copy_g2s(smem_u32(tiles + s * STAGE + 2 * A_BYTES), src, tile_bytes, full0 + 8 * s);
+                    const uint32_t stage_u32 = smem_u32(tiles + s * STAGE);
+                    if (DENSE) {
+                        // A_hi / A_lo: the tile's pixel patch shifted by the tap, 64 channels of the hi / lo half of the image rows
+                        const int tap = kb / cpb, ch = (kb - tap * cpb) * BKE;
+                        const int ky = tap / dg.kw, kx = tap - ky * dg.kw;
+                        mbar_arrive_expect_tx(full0 + 8 * s, tile_bytes + 2 * A_BYTES);
+                        tma_load_4d(stage_u32, &xmap, full0 + 8 * s, ch, x0 + kx, y0 + ky, img);
+                        tma_load_4d(stage_u32 + A_BYTES, &xmap, full0 + 8 * s, a.cin + ch, x0 + kx, y0 + ky, img);
+                    } else {
+                        mbar_arrive_expect_tx(full0 + 8 * s, tile_bytes);
+                    }
+                    bulk_copy_g2s(stage_u32 + 2 * A_BYTES, src, tile_bytes, full0 + 8 * s);
                 }
                 __syncwarp();
                 ++g;
@@ -483,17 +531,17 @@ int num_sms()
     return device_sms(pd);
 }
 
-template <int BN>
-int32_t launch_tc(const TcArgs &a, cudaStream_t stream)
+template <int BN, bool DENSE>
+int32_t launch_tc(const TcArgs &a, const CUtensorMap &xmap, const DenseGeo &dg, cudaStream_t stream)
 {
     static_assert(stages_for(BN) * stage_bytes(BN) + 2 * MAX_TAPS * BM * 4 + 1024 + 256 <= 227 * 1024, "shared memory budget");
     static PerDevice pd;
-    CPD_CUDA(opt_in_smem(pd, gather_gemm_tc_kernel<BN>, smem_bytes<BN>(MAX_TAPS)));
-    const long long tiles = div_up(a.m_out, BM) * (a.cout / BN);
+    CPD_CUDA(opt_in_smem(pd, gather_gemm_tc_kernel<BN, DENSE>, smem_bytes<BN>(DENSE ? 0 : MAX_TAPS)));
+    const long long tiles = (DENSE ? (long long)dg.n * dg.tiles_y * dg.tiles_x : div_up(a.m_out, BM)) * (a.cout / BN);
     const unsigned grid = (unsigned)(tiles < num_sms() ? tiles : num_sms());
-    gather_gemm_tc_kernel<BN><<<grid, NTHREADS, smem_bytes<BN>(a.K), stream>>>(a);
+    gather_gemm_tc_kernel<BN, DENSE><<<grid, DENSE ? NTHREADS_DENSE : NTHREADS_SP, smem_bytes<BN>(DENSE ? 0 : a.K), stream>>>(a, xmap, dg);
     count_launch();
-    return launch_status("cpd_gather_gemm[tcgen05]");
+    return launch_status(DENSE ? "cpd_conv2d[tcgen05+TMA]" : "cpd_gather_gemm[tcgen05]");
 }
 
 inline int bn_for(int cout) { return cout >= 256 ? 256 : cout; }
@@ -579,12 +627,88 @@ int32_t gather_gemm_tc(const void *xs, int32_t cin, const float *w, int32_t K, i
     if ((cin & (cin - 1)) == 0)
         for (cin_shift = 0; (1 << cin_shift) < cin; ++cin_shift) {}
     TcArgs a{bias, scale, shift, residual, reinterpret_cast<const uint8_t *>(xs), wsplit, nbr, tile_counter, tile_masks, out_rows, stats, y, m_out, cin, K, cout, relu, cin_shift};
+    static const CUtensorMap no_map{};
+    const DenseGeo no_geo{};
     switch (cout) {
-        case 16: return launch_tc<16>(a, stream);
-        case 32: return launch_tc<32>(a, stream);
-        case 64: return launch_tc<64>(a, stream);
-        case 128: return launch_tc<128>(a, stream);
-        default: return launch_tc<256>(a, stream);
+        case 16: return launch_tc<16, false>(a, no_map, no_geo, stream);
+        case 32: return launch_tc<32, false>(a, no_map, no_geo, stream);
+        case 64: return launch_tc<64, false>(a, no_map, no_geo, stream);
+        case 128: return launch_tc<128, false>(a, no_map, no_geo, stream);
+        default: return launch_tc<256, false>(a, no_map, no_geo, stream);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Dense stride-1 convolution over an NHWC image batch (the BEV backbone / CenterHead convs and their input-gradients).
+// ---------------------------------------------------------------------------------------------------------------
+bool conv2d_tc_supported(int32_t cin, int32_t kh, int32_t kw, int32_t cout)
+{
+    const long long K = (long long)kh * kw;
+    return cin >= BKE && cin % BKE == 0 && K >= 1 && K <= MAX_TAPS && K * cin <= 32ll * KBW * BKE &&
+           (cout == 16 || cout == 32 || cout == 64 || cout == 128 || (cout >= 256 && cout % 256 == 0 && cout <= 2048));
+}
+
+size_t conv2d_tc_workspace(int32_t cin, int32_t kh, int32_t kw, int32_t cout) { return gather_gemm_tc_workspace(cin, kh * kw, cout); }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {                       // the driver entry point, resolved at run time: the library does not link libcuda
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int32_t conv2d_tc(const void *xs, int32_t n, int32_t h, int32_t w_, int32_t cin, const float *w, int32_t kh, int32_t kw, int32_t pad,
+                  int32_t cout, const float *bias, const float *scale, const float *shift, const float *residual, int32_t relu,
+                  float *stats, int32_t clear_stats, float *y, int32_t out_h, int32_t out_w, int32_t out_sy, int32_t out_sx, int32_t out_oy,
+                  int32_t out_ox, void *ws, size_t ws_bytes, cudaStream_t stream)
+{
+    CPD_REQUIRE(conv2d_tc_supported(cin, kh, kw, cout), CPD_ERR_UNSUPPORTED, "cpd_conv2d: needs cin %% 64 == 0 and cout in {16,32,64,128,256k}");
+    CPD_REQUIRE((((uintptr_t)xs | (uintptr_t)w | (uintptr_t)y | (uintptr_t)bias | (uintptr_t)scale | (uintptr_t)shift | (uintptr_t)residual) & 15) == 0,
+                CPD_ERR_MISALIGNED, "cpd_conv2d: pointers must be 16-byte aligned");
+    CPD_REQUIRE(ws && ws_bytes >= conv2d_tc_workspace(cin, kh, kw, cout), CPD_ERR_WORKSPACE, "cpd_conv2d: workspace too small");
+    const int ho = h + 2 * pad - kh + 1, wo = w_ + 2 * pad - kw + 1;
+    CPD_REQUIRE(ho >= 1 && wo >= 1 && pad >= 0, CPD_ERR_BAD_ARG, "cpd_conv2d: empty output");
+    CPD_REQUIRE(out_sy >= 1 && out_sx >= 1 && out_oy >= 0 && out_ox >= 0 && (ho - 1) * out_sy + out_oy < out_h && (wo - 1) * out_sx + out_ox < out_w,
+                CPD_ERR_BAD_ARG, "cpd_conv2d: output placement outside the (out_h, out_w) map");
+    CPD_REQUIRE((long long)n * out_h * out_w < (1ll << 31) && (long long)n * h * w_ < (1ll << 31), CPD_ERR_UNSUPPORTED, "cpd_conv2d: image batch too large");
+    EncodeTiledFn enc = encode_tiled();
+    CPD_REQUIRE(enc, CPD_ERR_CUDA, "cpd_conv2d: cuTensorMapEncodeTiled is not available from this driver");
+    // split-row image as a 4-D bf16 tensor [n][h][w][2 cin] (row = hi(cin) | lo(cin)); box = 64 channels x DT_W x DT_H pixels
+    CUtensorMap xmap;
+    const cuuint64_t dims[4] = {(cuuint64_t)(2 * cin), (cuuint64_t)w_, (cuuint64_t)h, (cuuint64_t)n};
+    const cuuint64_t strides[3] = {(cuuint64_t)cin * 4, (cuuint64_t)cin * 4 * w_, (cuuint64_t)cin * 4 * w_ * h};
+    const cuuint32_t box[4] = {(cuuint32_t)BKE, (cuuint32_t)DT_W, (cuuint32_t)DT_H, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(xs), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CPD_REQUIRE(r == CUDA_SUCCESS, CPD_ERR_CUDA, "cpd_conv2d: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    unsigned int *tile_counter = reinterpret_cast<unsigned int *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    uint8_t *wsplit = reinterpret_cast<uint8_t *>(tile_counter) + 256;
+    const int K = kh * kw, Kf = K * cin, n_kb = Kf / BKE;
+    static const int bn_wide = getenv("CPD_DENSE_BN") ? atoi(getenv("CPD_DENSE_BN")) : 256;      // tuning knob: N tile for cout >= 256
+    const int bn = cout >= 256 ? (bn_wide == 128 ? 128 : 256) : cout;
+    const long long chunks = (long long)n_kb * cout * 8;
+    weight_split_kernel<<<(unsigned)div_up(chunks, 256), 256, 0, stream>>>(w, cout, Kf, n_kb, bn, wsplit, clear_stats ? stats : nullptr, tile_counter);
+    count_launch();
+    int cin_shift = -1;
+    TcArgs a{bias, scale, shift, residual, reinterpret_cast<const uint8_t *>(xs), wsplit, nullptr, tile_counter, nullptr, nullptr, stats, y,
+             (long long)n * ho * wo, cin, K, cout, relu, cin_shift};
+    DenseGeo dg{n, h, w_, ho, wo, kh, kw, pad, (int)div_up(wo, DT_W), (int)div_up(ho, DT_H), out_h, out_w, out_sy, out_sx, out_oy, out_ox};
+    switch (bn) {
+        case 16: return launch_tc<16, true>(a, xmap, dg, stream);
+        case 32: return launch_tc<32, true>(a, xmap, dg, stream);
+        case 64: return launch_tc<64, true>(a, xmap, dg, stream);
+        case 128: return launch_tc<128, true>(a, xmap, dg, stream);
+        default: return launch_tc<256, true>(a, xmap, dg, stream);
     }
 }
 

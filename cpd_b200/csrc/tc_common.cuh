@@ -121,6 +121,18 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t smem_dst, const void *gme
                  "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// ---- tiled TMA load of a 4-D box (tensor map built by cuTensorMapEncodeTiled; coordinates innermost first; out-of-range
+//      elements -- negative coordinates included -- are written as zeros and still count towards complete_tx) ----
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const void *tensor_map, uint32_t bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_dst), "l"(tensor_map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void *tensor_map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tensor_map) : "memory");
+}
+
 // ---- 16-byte asynchronous copies global -> shared (LDGSTS); src_size = 0 zero-fills the destination ----
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gmem_src, uint32_t src_size)
 {

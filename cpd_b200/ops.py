@@ -286,6 +286,103 @@ def gather_wgrad(x, dy, nbr, want_bias=False, algo=ALGO_AUTO, tap_major=False, x
     return dw, db
 
 
+# ------------------------------------------------------------------------------------
+# dense stride-1 convolutions on the TMA-fed tcgen05 kernel (no neighbour table)
+# ------------------------------------------------------------------------------------
+_CONV2D_OK = {}
+
+
+def conv2d_ok(cin, k, cout):
+    """Shapes cpd_conv2d_fwd takes (cin % 64 == 0, cout in {16, 32, 64, 128, 256 j})."""
+    key = (int(cin), int(k), int(cout))
+    if key not in _CONV2D_OK:
+        _CONV2D_OK[key] = bool(_lib.lib().cpd_conv2d_supported(key[0], key[1], key[1], key[2]))
+    return _CONV2D_OK[key]
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0
+
+
+def _prof_end(e0, **meta):
+    if e0 is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        PROFILE.append((e0, e1, meta))
+
+
+def conv2d_fwd(x_split, n, h, w, weight, k, pad, bias=None, scale=None, shift=None, residual=None, relu=False, stats=None):
+    """y (n*ho*wo, cout) = epi(conv(x, weight)); x_split: split-row image of the NHWC rows (n*h*w, 2, cin);
+    weight (cout, k*k, cin)."""
+    _need_cuda(x_split, weight)
+    L = _lib.lib()
+    cout, cin = weight.shape[0], weight.shape[-1]
+    weight = _f32c(weight).view(cout, -1, cin)
+    assert weight.shape[1] == k * k and x_split.shape == (n * h * w, 2, cin) and x_split.is_contiguous()
+    ho, wo = h + 2 * pad - k + 1, w + 2 * pad - k + 1
+    y = torch.empty((n * ho * wo, cout), dtype=torch.float32, device=weight.device)
+    residual = _f32c(residual) if residual is not None else None
+    wsb = L.cpd_conv2d_workspace_bytes(cin, k, k, cout)
+    ws = _ws(wsb, weight.device)
+    e0 = _prof_begin()
+    _lib.check(L.cpd_conv2d_fwd(_ptr(x_split), n, h, w, cin, _ptr(weight), k, k, pad, cout, _ptr(bias), _ptr(scale), _ptr(shift),
+                                _ptr(residual), int(bool(relu)), _ptr(stats), _ptr(y), _ptr(ws), wsb, _stream()), "cpd_conv2d_fwd")
+    _prof_end(e0, kind="conv2d", m_in=n * h * w, m_out=n * ho * wo, cin=cin, cout=cout, K=k * k, P=n * ho * wo * k * k, residual=residual is not None)
+    return y
+
+
+def conv2d_dgrad(dy_split, n, h, w, cin, weight, k, pad):
+    """dx (n*h*w, cin) of conv2d_fwd; dy_split: split-row image of dy (n*ho*wo, 2, cout); weight (cout, k*k, cin)."""
+    _need_cuda(dy_split, weight)
+    L = _lib.lib()
+    cout = weight.shape[0]
+    weight = _f32c(weight).view(cout, -1, cin)
+    ho, wo = h + 2 * pad - k + 1, w + 2 * pad - k + 1
+    assert dy_split.shape == (n * ho * wo, 2, cout) and dy_split.is_contiguous()
+    dx = torch.empty((n * h * w, cin), dtype=torch.float32, device=weight.device)
+    wsb = L.cpd_conv2d_dgrad_workspace_bytes(cin, k, k, cout)
+    ws = _ws(wsb, weight.device)
+    e0 = _prof_begin()
+    _lib.check(L.cpd_conv2d_dgrad(_ptr(dy_split), n, h, w, cin, _ptr(weight), k, k, pad, cout, _ptr(dx), _ptr(ws), wsb, _stream()),
+               "cpd_conv2d_dgrad")
+    _prof_end(e0, kind="conv2d", m_in=n * ho * wo, m_out=n * h * w, cin=cout, cout=cin, K=k * k, P=n * h * w * k * k, residual=False)
+    return dx
+
+
+def conv2d_wgrad(x_split, dy_split, n, h, w, k, pad):
+    """dw (cout, k*k, cin) of conv2d_fwd from the two split-row images (pixel table built in the call's workspace)."""
+    _need_cuda(x_split, dy_split)
+    L = _lib.lib()
+    cin, cout = x_split.shape[2], dy_split.shape[2]
+    dw = torch.empty((cout, k * k, cin), dtype=torch.float32, device=x_split.device)
+    wsb = L.cpd_conv2d_wgrad_workspace_bytes(n, h, w, k, k, pad)
+    ws = _ws(wsb, x_split.device)
+    _lib.check(L.cpd_conv2d_wgrad(_ptr(x_split), _ptr(dy_split), n, h, w, cin, k, k, pad, cout, _ptr(dw), _ptr(ws), wsb, _stream()),
+               "cpd_conv2d_wgrad")
+    return dw
+
+
+def convt2d_fwd(x_split, n, h, w, weight, s, scale=None, shift=None, relu=False, stats=None):
+    """nn.ConvTranspose2d with kernel == stride == s: y (n*h*s*w*s, cout); weight in the torch layout (cin, cout, s, s)."""
+    _need_cuda(x_split, weight)
+    L = _lib.lib()
+    cin, cout = weight.shape[0], weight.shape[1]
+    weight = _f32c(weight)
+    assert x_split.shape == (n * h * w, 2, cin) and x_split.is_contiguous() and weight.shape[2] == weight.shape[3] == s
+    y = torch.empty((n * h * s * w * s, cout), dtype=torch.float32, device=weight.device)
+    wsb = L.cpd_convt2d_workspace_bytes(cin, s, cout)
+    ws = _ws(wsb, weight.device)
+    e0 = _prof_begin()
+    _lib.check(L.cpd_convt2d_fwd(_ptr(x_split), n, h, w, cin, _ptr(weight), s, cout, _ptr(scale), _ptr(shift), int(bool(relu)), _ptr(stats),
+                                 _ptr(y), _ptr(ws), wsb, _stream()), "cpd_convt2d_fwd")
+    _prof_end(e0, kind="convt2d", m_in=n * h * w, m_out=n * h * s * w * s, cin=cin, cout=cout, K=1, P=n * h * s * w * s, residual=False)
+    return y
+
+
 def weight_transpose(w, flip_taps=False):
     """(cout, K, cin) -> (cin, K, cout), optionally reversing taps."""
     _need_cuda(w)

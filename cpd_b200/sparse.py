@@ -162,10 +162,19 @@ class _GatherConv(torch.autograd.Function):
         cout, cin, K = weight.shape[0], weight.shape[-1], rb.nbr_fwd.shape[1]
         # narrow outputs (the 1-3 channel CenterHead maps): zero-pad the output channels so the tensor-core kernels apply
         ctx.pad_out = algo != ops.ALGO_SIMT and cout < 8 and cin % 8 == 0 and not want_stats
+        # dense stride-1 convs (rb.geo: a pixel table of the BEV maps) run table-free on the TMA-fed kernel
+        geo = getattr(rb, "geo", None) if algo != ops.ALGO_SIMT else None
+        if geo is not None and geo["stride"] != 1:
+            geo = None
         if ctx.pad_out:
             wp = torch.nn.functional.pad(weight.reshape(cout, K, cin), (0, 0, 0, 0, 0, 16 - cout))
             bp = torch.nn.functional.pad(bias, (0, 16 - cout)) if bias is not None else None
             ctx.xs = None
+            if geo is not None and ops.conv2d_ok(cin, geo["k"], 16):
+                xs = _carried_split(x)
+                if xs is None:
+                    xs = ops.split_rows(x)
+                return ops.conv2d_fwd(xs, geo["n"], geo["h"], geo["w"], wp, geo["k"], geo["pad"], bias=bp)[:, :cout].contiguous()
             return ops.gather_gemm(x, wp, rb.nbr_fwd, bias=bp, algo=algo)[:, :cout].contiguous()
         # the split-row image of x (bf16 hi | lo, the tcgen05 operand format) is built once and shared by the
         # forward GEMM and the weight-gradient
@@ -177,7 +186,9 @@ class _GatherConv(torch.autograd.Function):
                 xs = ops.split_rows(x)
         ctx.xs = xs if needs_grad else None
         srt = rb.sorted_table("fwd", cin) if (xs is not None and ops.tc_gemm_ok(cin, K, cout)) else None
-        if srt is not None:                                # rows in tap-pattern order, epilogue scatters them back
+        if geo is not None and xs is not None and ops.conv2d_ok(cin, geo["k"], cout):
+            y = ops.conv2d_fwd(xs, geo["n"], geo["h"], geo["w"], weight, geo["k"], geo["pad"], bias=bias, stats=stats)
+        elif srt is not None:                                # rows in tap-pattern order, epilogue scatters them back
             y = ops.gather_gemm(x, weight, srt[0], bias=bias, stats=stats, algo=algo, x_split=xs, tile_masks=srt[2], out_rows=srt[1])
         else:
             y = ops.gather_gemm(x, weight, rb.nbr_fwd, bias=bias, stats=stats, algo=algo, x_split=xs, tile_masks=rb.masks_fwd)
@@ -217,7 +228,10 @@ class _GatherConv(torch.autograd.Function):
                     dys = ops.split_rows(dy)
         if ctx.needs_input_grad[0]:
             tc_dgrad = dys is not None and ops.tc_gemm_ok(cout, K, cin)
-            if rb.kind == "subm":
+            geo = getattr(rb, "geo", None) if ctx.algo != ops.ALGO_SIMT else None
+            if geo is not None and geo["stride"] == 1 and dys is not None and ops.conv2d_ok(cout, geo["k"], cin):
+                dx = ops.conv2d_dgrad(dys, geo["n"], geo["h"], geo["w"], cin, weight, geo["k"], geo["pad"])      # table-free, TMA-fed
+            elif rb.kind == "subm":
                 wt = ops.weight_transpose(weight, flip_taps=True)
                 srt = rb.sorted_table("fwd", cout) if tc_dgrad else None
                 if srt is not None:

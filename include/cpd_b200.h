@@ -204,6 +204,39 @@ CPD_API int32_t cpd_conv2d_table(int32_t n, int32_t h, int32_t w, int32_t kh, in
                          int32_t pad, int32_t transposed, int32_t ho, int32_t wo, int32_t *nbr,
                          cpd_stream_t stream);
 
+/* ---------------------------------------------------------------------------------
+ * Dense 2-D convolutions over NHWC image batches, stride 1: nn.Conv2d / nn.ConvTranspose2d of
+ * cpd/models/backbones_2d/base_bev_backbone.py:31-59 and cpd/models/dense_heads/center_head.py:11-45,73-80
+ * (cuDNN in the reference).  Same arithmetic and epilogue as cpd_gather_gemm (bf16x3 on tcgen05), but the A operand
+ * of tap (ky, kx) is the output tile's 16 x 8 pixel patch shifted by the tap: one tiled TMA load
+ * (cp.async.bulk.tensor.4d over the split-row image seen as [n][h][w][2 cin] bf16) per (tap, 64-channel block, hi / lo),
+ * with the zero padding and the image border filled by the TMA unit -- no neighbour table, no gather.
+ * x_split: split-row image (cpd_split_rows) of x (n*h*w, cin); wgt: (cout, kh*kw, cin); y: (n*ho*wo, cout),
+ * ho = h + 2 pad - kh + 1.  Needs cin % 64 == 0 and cout in {16, 32, 64, 128, 256 j} (cpd_conv2d_supported); the other
+ * dense shapes of the model (stride 2, 1-3 output channels) run through cpd_conv2d_table + cpd_gather_gemm.
+ * --------------------------------------------------------------------------------- */
+CPD_API int32_t cpd_conv2d_supported(int32_t cin, int32_t kh, int32_t kw, int32_t cout);
+CPD_API size_t cpd_conv2d_workspace_bytes(int32_t cin, int32_t kh, int32_t kw, int32_t cout);
+CPD_API int32_t cpd_conv2d_fwd(const void *x_split, int32_t n, int32_t h, int32_t w, int32_t cin, const float *wgt, int32_t kh,
+                       int32_t kw, int32_t pad, int32_t cout, const float *bias, const float *scale, const float *shift,
+                       const float *residual, int32_t relu, float *stats, float *y, void *ws, size_t ws_bytes, cpd_stream_t stream);
+/* input-gradient dx (n*h*w, cin) from the split-row image of dy (n*ho*wo, cout): the same kernel with the flipped,
+ * transposed weights (built in the workspace) and padding k - 1 - pad.  Needs cout % 64 == 0, cin in {16, ..., 256 j}. */
+CPD_API size_t cpd_conv2d_dgrad_workspace_bytes(int32_t cin, int32_t kh, int32_t kw, int32_t cout);
+CPD_API int32_t cpd_conv2d_dgrad(const void *dy_split, int32_t n, int32_t h, int32_t w, int32_t cin, const float *wgt, int32_t kh,
+                         int32_t kw, int32_t pad, int32_t cout, float *dx, void *ws, size_t ws_bytes, cpd_stream_t stream);
+/* weight gradient dw (cout, kh*kw, cin), overwritten: the row-stationary tcgen05 kernel of cpd_gather_wgrad over a pixel
+ * table generated into the workspace (callers that keep the table use cpd_gather_wgrad directly). */
+CPD_API size_t cpd_conv2d_wgrad_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t kh, int32_t kw, int32_t pad);
+CPD_API int32_t cpd_conv2d_wgrad(const void *x_split, const void *dy_split, int32_t n, int32_t h, int32_t w, int32_t cin, int32_t kh,
+                         int32_t kw, int32_t pad, int32_t cout, float *dw, void *ws, size_t ws_bytes, cpd_stream_t stream);
+/* nn.ConvTranspose2d with kernel == stride == s (base_bev_backbone.py:48-59): s*s 1x1 GEMMs whose epilogues write the
+ * pixel-shuffled (n, h*s, w*s, cout) map directly.  wgt: torch layout (cin, cout, s, s).  stats accumulate over the whole map. */
+CPD_API size_t cpd_convt2d_workspace_bytes(int32_t cin, int32_t s, int32_t cout);
+CPD_API int32_t cpd_convt2d_fwd(const void *x_split, int32_t n, int32_t h, int32_t w, int32_t cin, const float *wgt, int32_t s,
+                        int32_t cout, const float *scale, const float *shift, int32_t relu, float *stats, float *y, void *ws,
+                        size_t ws_bytes, cpd_stream_t stream);
+
 /* SparseConvTensor.dense() fused with HeightCompression's view
  * (cpd/models/backbones_2d/map_to_bev/height_compression.py:136-138): scatter (m, c)
  * rows into a zeroed image.  channels_last == 0: out is (B, C, D, H, W) as upstream;
