@@ -71,7 +71,9 @@ class DenseConv2d(nn.Module):
         self.in_channels, self.out_channels = in_channels, out_channels
         self.k, self.stride, self.padding = int(kernel_size), int(stride), int(padding)
         self.algo = ops.ALGO_AUTO if algo is None else algo
-        self.weight = nn.Parameter(torch.empty(out_channels, in_channels, self.k, self.k))
+        # nn.Conv2d's (cout, cin, kh, kw) SHAPE (checkpoints load unchanged) over (cout, kh, kw, cin) MEMORY (channels_last):
+        # the kernels' (cout, K, cin) operand is then a view -- no per-step permute copy forward, none for the gradient
+        self.weight = nn.Parameter(torch.empty(out_channels, self.k, self.k, in_channels).permute(0, 3, 1, 2))
         self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
         nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
         if bias:
@@ -109,6 +111,7 @@ class _ConvT2d(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, n, h, w, want_stats):
+        ctx.set_materialize_grads(False)
         s = weight.shape[2]
         xs = _carried_split(x)
         if xs is None:
@@ -124,6 +127,8 @@ class _ConvT2d(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, *unused):
+        if dy is None:
+            return None, None, None, None, None, None
         x, weight = ctx.saved_tensors
         n, h, w, s = ctx.geo
         cin, cout = weight.shape[0], weight.shape[1]

