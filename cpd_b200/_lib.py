@@ -17,6 +17,7 @@ SIGNATURES = {
     "cpd_launch_count": (_i64, []),
     "cpd_voxelize_workspace_bytes": (_sz, [_i64, _i32, _i32, _i64]),
     "cpd_voxelize": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cpd_voxelize_cpu": (_i64, [_vp, _i64, _i32, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
     "cpd_coord_hash_bytes": (_sz, [_i64]),
     "cpd_coord_hash_build": (_i32, [_vp, _i64, _vp, _i32, _vp, _sz, _vp]),
     "cpd_rulebook_subm": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _sz, _vp, _vp]),

@@ -18,6 +18,9 @@
 //   5. vox_fill     : one thread per (row, feature): gathers the <= max_pts points, writes
 //                     the zero-padded voxel block and the mean.
 // HBM traffic: N*C*4 read + M*(max_pts*C*4 + 16 + 4 + C*4) written, plus the table.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace cpd {
@@ -269,4 +272,64 @@ extern "C" int32_t cpd_voxelize(const float *points, int64_t n, int32_t c, const
         count_launch(1);
     }
     return launch_status("cpd_voxelize");
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host entry with the same semantics for ONE frame: the reference calls
+// Point2VoxelCPU3d.point_to_voxel inside Dataset.__getitem__, i.e. in forked DataLoader worker processes
+// (cpd/datasets/processor/data_processor.py:133-144), where CUDA must not be touched.  Sequential first-come
+// grouping exactly as upstream; an open-addressing table over the occupied cells replaces upstream's dense
+// 92.7 M-cell lookup grid.  All pointers are HOST pointers.  Returns the number of voxels (>= 0) or a cpd_status (< 0).
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int64_t cpd_voxelize_cpu(const float *points, int64_t n, int32_t c, const float *range6, const float *vsize3,
+                                    int32_t max_pts, int64_t max_voxels, float *voxels, int32_t *coords_zyx, int32_t *num_points)
+{
+    CPD_REQUIRE(n >= 0 && c >= 3 && max_pts >= 1 && max_voxels >= 0, CPD_ERR_BAD_ARG, "cpd_voxelize_cpu: bad n/c/max_pts");
+    CPD_REQUIRE((points || n == 0) && range6 && vsize3 && voxels && coords_zyx && num_points, CPD_ERR_BAD_ARG, "cpd_voxelize_cpu: null argument");
+    long long grid[3];
+    for (int j = 0; j < 3; ++j) {
+        grid[j] = (long long)roundf((range6[3 + j] - range6[j]) / vsize3[j]);
+        CPD_REQUIRE(grid[j] > 0, CPD_ERR_BAD_ARG, "cpd_voxelize_cpu: empty grid");
+    }
+    uint64_t cap = 1024;
+    while (cap < (uint64_t)n * 2 + 2) cap <<= 1;
+    long long *keys = (long long *)malloc(sizeof(long long) * cap);
+    int32_t *vals = (int32_t *)malloc(sizeof(int32_t) * cap);
+    if (!keys || !vals) { free(keys); free(vals); set_error("cpd_voxelize_cpu: out of host memory"); return CPD_ERR_BAD_ARG; }
+    for (uint64_t i = 0; i < cap; ++i) keys[i] = -1;
+    int64_t nvox = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const float *p = points + i * c;
+        int cell[3];
+        bool ok = true;
+        for (int j = 0; j < 3 && ok; ++j) {
+            const float t = floorf((p[j] - range6[j]) / vsize3[j]);       // fp32 subtract, divide, floor -- as upstream and as the kernel
+            ok = (t >= 0.0f) && (t < (float)grid[j]);
+            cell[j] = (int)t;
+        }
+        if (!ok) continue;
+        const long long key = ((long long)cell[2] * grid[1] + cell[1]) * grid[0] + cell[0];
+        uint64_t h = (uint64_t)key * 0x9E3779B97F4A7C15ull;
+        uint64_t s = (h >> 20) & (cap - 1);
+        while (keys[s] != -1 && keys[s] != key) s = (s + 1) & (cap - 1);
+        int32_t vid;
+        if (keys[s] == -1) {
+            if (nvox >= max_voxels) continue;                               // at capacity: new cells are dropped
+            keys[s] = key;
+            vid = vals[s] = (int32_t)nvox++;
+            coords_zyx[3 * vid] = cell[2]; coords_zyx[3 * vid + 1] = cell[1]; coords_zyx[3 * vid + 2] = cell[0];
+            num_points[vid] = 0;
+            memset(voxels + (size_t)vid * max_pts * c, 0, sizeof(float) * (size_t)max_pts * c);
+        } else {
+            vid = vals[s];
+        }
+        const int32_t k = num_points[vid];
+        if (k < max_pts) {
+            memcpy(voxels + ((size_t)vid * max_pts + k) * c, p, sizeof(float) * (size_t)c);
+            num_points[vid] = k + 1;
+        }
+    }
+    free(keys); free(vals);
+    return nvox;
 }

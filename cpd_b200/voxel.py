@@ -42,6 +42,11 @@ def _device():
 
 
 class Point2VoxelCPU3d:
+    """spconv.utils.Point2VoxelCPU3d of the shim.  Like upstream it is a HOST routine (cpd_voxelize_cpu: numpy in, numpy
+    out, no CUDA): the reference calls it inside Dataset.__getitem__, i.e. in forked DataLoader worker processes
+    (data_processor.py:133-144), where a CUDA context must not be created.  The hot path does not go through here:
+    voxelize_batch / cpd_voxelize take the raw device points in the main process."""
+
     def __init__(self, vsize_xyz, coors_range_xyz, num_point_features, max_num_points_per_voxel, max_num_voxels):
         self.vsize = [float(v) for v in vsize_xyz]
         self.coors_range = [float(v) for v in coors_range_xyz]
@@ -51,17 +56,24 @@ class Point2VoxelCPU3d:
         self.grid_size = [int(round((self.coors_range[3 + i] - self.coors_range[i]) / self.vsize[i])) for i in range(3)]
 
     def point_to_voxel(self, pc):
+        import ctypes as C
+
+        from . import _lib
         arr = pc.numpy_view() if isinstance(pc, TvTensor) else np.asarray(pc)
         arr = np.ascontiguousarray(arr, dtype=np.float32)
         assert arr.ndim == 2 and arr.shape[1] == self.num_point_features
-        dev = _device()
-        pts = torch.from_numpy(arr).to(dev, non_blocking=False)
-        out = ops.voxelize(pts, [0, arr.shape[0]], self.coors_range, self.vsize, self.max_pts, self.max_voxels,
-                           want_voxels=True, want_mean=False)
-        voxels = out["voxels"].cpu().numpy()
-        coords = out["coords"][:, 1:].contiguous().cpu().numpy()      # per-frame API: (M,3) zyx
-        num = out["num"].cpu().numpy()
-        return TvTensor(voxels), TvTensor(coords), TvTensor(num)
+        n, c = arr.shape
+        cap = max(1, min(n, self.max_voxels))
+        voxels = np.empty((cap, self.max_pts, c), np.float32)
+        coords = np.empty((cap, 3), np.int32)
+        num = np.empty((cap,), np.int32)
+        rng = np.asarray(self.coors_range, np.float32)
+        vs = np.asarray(self.vsize, np.float32)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        m = _lib.lib().cpd_voxelize_cpu(vp(arr), n, c, vp(rng), vp(vs), self.max_pts, self.max_voxels, vp(voxels), vp(coords), vp(num))
+        if m < 0:
+            _lib.check(int(m), "cpd_voxelize_cpu")
+        return TvTensor(voxels[:m]), TvTensor(coords[:m]), TvTensor(num[:m])
 
 
 class PointToVoxel:

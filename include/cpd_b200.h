@@ -72,6 +72,13 @@ CPD_API int32_t cpd_voxelize(const float *points, int64_t n_points, int32_t c,
                      float *voxels, int32_t *coords_bzyx, int32_t *num_points, float *mean,
                      int32_t *counts, void *ws, size_t ws_bytes, cpd_stream_t stream);
 
+/* Host (CPU) entry with the same semantics for ONE frame, all pointers HOST pointers: the reference calls the
+ * voxelizer inside Dataset.__getitem__, i.e. in forked DataLoader workers (data_processor.py:133-144) where CUDA must not be
+ * touched.  voxels (cap, max_pts, c), coords_zyx (cap, 3), num_points (cap,), cap >= min(n, max_voxels).  Returns the number
+ * of voxels (>= 0) or a cpd_status (< 0).  This is the shim's spconv.utils.Point2VoxelCPU3d; the hot path uses cpd_voxelize. */
+CPD_API int64_t cpd_voxelize_cpu(const float *points, int64_t n_points, int32_t c, const float *range6_host, const float *vsize3_host,
+                         int32_t max_pts, int64_t max_voxels, float *voxels, int32_t *coords_zyx, int32_t *num_points);
+
 /* ---------------------------------------------------------------------------------
  * Rulebooks.  Replace the indice-pair generation hidden inside spconv.SubMConv3d /
  * spconv.SparseConv3d (call sites cpd/models/backbones_3d/spconv_backbone.py:17,20-21,
