@@ -31,7 +31,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="detector_train", choices=["detector_train", "backbone_fwd"])
+    ap.add_argument("--workload", default="detector_train", choices=["detector_train", "backbone_fwd", "stress"])
     ap.add_argument("--batch", type=int, default=4, help="frames per step per GPU (CPD trains with 4)")
     ap.add_argument("--points", type=int, default=160000, help="points per frame")
     ap.add_argument("--pool", type=int, default=2, help="distinct batches cycled through")
@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--prefetch", action="store_true", help="run the input stage (voxelize + rulebooks) one step ahead on a side stream "
                                                             "(detector.prepare) instead of inline")
     a = ap.parse_args()
+    if a.workload == "stress" and a.points == 160000:
+        a.points = 300000                      # BASELINE configs[4]: 300k points / 200k active voxels per frame
     a.no_prefetch = not a.prefetch
     if a.prefetch:
         # the side stream has its own caching-allocator pool; with the default allocator its growth (cudaMalloc per new
@@ -48,6 +50,10 @@ def parse():
 
 
 def workload_name(a):
+    if a.workload == "stress":
+        return (f"dense-scene stress: {a.points // 1000}k pts/frame at ~200k active voxels/frame, bs={a.batch}/GPU: voxelize + the whole "
+                f"rulebook chain of VoxelResBackBone8x + SubM gather-GEMM C->C sweep (C = 16,32,64,128 on the 200k-voxel level and on the "
+                f"level each width runs at) + dense() [BASELINE configs[4]]")
     if a.workload == "backbone_fwd":
         return (f"CPD VoxelBackBone8x fwd (voxelize+MeanVFE+12 sparse convs+BEV dense), {a.points // 1000}k pts/frame, "
                 f"bs={a.batch}/GPU [BASELINE configs[1]]")
@@ -56,9 +62,80 @@ def workload_name(a):
             f"[BASELINE configs[2]; configs[3] under torchrun]")
 
 
-def make_frames(rank, count, points):
-    from cpd_b200.synth import synth_scan
+def make_frames(rank, count, points, dense=False):
+    from cpd_b200.synth import synth_dense_scan, synth_scan
+    if dense:
+        return [synth_dense_scan(points, 1000 * rank + i)[0] for i in range(count)]
     return [synth_scan(points, 1000 * rank + i) for i in range(count)]
+
+
+class StressSweep:
+    """BASELINE configs[4]: the front end and the gather/scatter stage alone, on dense scenes.  One step = voxelize the batch,
+    build every rulebook of the VoxelResBackBone8x chain (SubM tables, strided output sets + tables, tap-pattern order,
+    tile masks), run SubM C->C gather-GEMMs for C in {16, 32, 64, 128} on the stage-1 (200 k voxels / frame) table and on
+    the level each width runs at in the model, and scatter the last level to the dense BEV map."""
+    CH = (16, 32, 64, 128)
+    PADS = (1, 1, (0, 1, 1))
+
+    def __init__(self, dev):
+        import torch
+        self.dev = dev
+        g = torch.Generator(device="cpu").manual_seed(7)
+        self.w = {c: (torch.randn(c, 27, c, generator=g) * (27 * c) ** -0.5).to(dev) for c in self.CH}
+        self.feat = {}
+        self.info = {}
+        from cpd_b200 import sparse as sp
+        self.subm = [sp.SubMConv3d(c, c, 3, bias=False, indice_key=f"subm{i}") for i, c in enumerate(self.CH)]      # geometry only
+        self.down = [sp.SparseConv3d(self.CH[i], self.CH[i + 1], 3, stride=2, padding=self.PADS[i], bias=False, indice_key=f"down{i}")
+                     for i in range(3)]
+        self.out = sp.SparseConv3d(128, 128, (3, 1, 1), stride=(2, 1, 1), padding=0, bias=False, indice_key="out")
+
+    def _x(self, key, m, c):
+        import torch
+        k = (key, m, c)
+        if k not in self.feat:                     # synthetic features of the level's size, made once per distinct batch
+            g = torch.Generator(device="cpu").manual_seed(m % 65521 + c)
+            x = torch.randn(m, c, generator=g).to(self.dev)
+            self.feat[k] = (x, None)
+        x, xs = self.feat[k]
+        return x, xs
+
+    def step(self, points):
+        import torch
+        from cpd_b200 import ops, sparse as sp, voxel
+        from cpd_b200.synth import PC_RANGE, VOXEL_SIZE
+        bd = voxel.voxelize_batch([p if p.is_cuda else p.to(self.dev, non_blocking=True) for p in points], PC_RANGE, VOXEL_SIZE)
+        bs = len(points)
+        c1 = bd["voxel_coords"]
+        key = ((c1[:, 0].long() * 41 + c1[:, 1]) * 1504 + c1[:, 2]) * 1504 + c1[:, 3]
+        coords = c1.index_select(0, torch.argsort(key))
+        t = sp.SparseConvTensor(None, coords, [41, 1504, 1504], bs)
+        acc = bd["voxel_features"].sum()
+        levels = []
+        for s in range(4):
+            rb, _ = self.subm[s].get_rulebook(t)
+            m = t.indices.shape[0]
+            levels.append((m, rb))
+            widths = self.CH if s == 0 else (self.CH[s],)
+            for c in widths:
+                x, _ = self._x(s, m, c)
+                xs = ops.split_rows(x)
+                srt = rb.sorted_table("fwd", c)
+                if srt is not None:
+                    y = ops.gather_gemm(x, self.w[c], srt[0], x_split=xs, tile_masks=srt[2], out_rows=srt[1])
+                else:
+                    y = ops.gather_gemm(x, self.w[c], rb.nbr_fwd, x_split=xs, tile_masks=rb.masks_fwd)
+                acc = acc + y[0, 0]
+            if s < 3:
+                rbd, oh = self.down[s].get_rulebook(t)
+                rbd.sorted_table("fwd", self.CH[s]); rbd.bwd_sorted(self.CH[s + 1])
+                t = self.down[s]._wrap_output(t, rbd, oh, None)
+        rbo, oh = self.out.get_rulebook(t)
+        to = self.out._wrap_output(t, rbo, oh, None)
+        x, _ = self._x("out", to.indices.shape[0], 128)
+        dense = ops.sparse_to_dense(x, to.indices, bs, to.spatial_shape, channels_last=True)
+        self.info = {"voxels_per_level": [m for m, _ in levels] + [int(to.indices.shape[0])]}
+        return acc + dense[0, 0, 0, 0], to.replace_feature(x)
 
 
 def make_net(device):
@@ -143,8 +220,10 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
     train = a.workload == "detector_train"
+    if a.workload == "stress":
+        a.pool = 1                                 # generating a 200k-voxel scene takes seconds: one batch, L2 flushed between steps
     nfr = a.batch * a.pool
-    frames = make_frames(rank, nfr, a.points)
+    frames = make_frames(rank, nfr, a.points, dense=a.workload == "stress")
     host = [torch.from_numpy(f).pin_memory() for f in frames]
     resident = [h.to(dev) for h in host]
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
@@ -190,6 +269,13 @@ def run_ours(a):
         run_host = lambda i: step(i, host, host1, host_gt)         # .to(device, non_blocking) happens inside the detector
         ctx = torch.enable_grad()
         h2d = sum(h.numel() * 4 for h in host[:a.batch]) + sum(h.numel() * 4 for h in host1[:a.batch]) + host_gt[0].numel() * 4
+    elif a.workload == "stress":
+        net = None
+        sweep = StressSweep(dev)
+        run_resident = lambda i: sweep.step(batch_of(i, resident))
+        run_host = lambda i: sweep.step(batch_of(i, host))
+        ctx = torch.no_grad()
+        h2d = sum(h.numel() * 4 for h in host[:a.batch])
     else:
         net = make_net(dev)
         to_bev = backbone.HeightCompression()
@@ -268,23 +354,50 @@ def run_ours(a):
     total_ms, e2e_ms = float(t[0]), float(t[1])
     frames_total = a.batch * a.steps * world
 
-    # ---- roofline of the dominant kernel family (gather-GEMM), per layer shape ----
+    # ---- roofline of the dominant kernel family (gather-GEMM), per layer shape; front-end (voxelizer, rulebooks) entries ----
     hbm, bf16, src = peaks()
-    groups, pcache = {}, {}
+    groups, front, pcache, stages = {}, {}, {}, {}
+
+    def pairs(t):
+        if id(t) not in pcache:
+            pcache[id(t)] = int((t >= 0).sum().item())
+        return pcache[id(t)]
+
     for e0, e1, m in prof:
-        key = (m["kind"], m["cin"], m["cout"], m["K"])
-        if "P" in m:                                     # dense TMA convs: every tap of every output pixel
-            P = m["P"]
-        else:
-            nid = id(m["nbr"])
-            if nid not in pcache:
-                pcache[nid] = int((m["nbr"] >= 0).sum().item())
-            P = pcache[nid]
-        g = groups.setdefault(key, dict(ms=0.0, n=0, bytes=0.0, flops=0.0))
-        g["ms"] += e0.elapsed_time(e1); g["n"] += 1
-        g["bytes"] += 4.0 * (m["m_in"] * m["cin"] + m["m_out"] * m["cout"]) + 8.0 * P + 4.0 * m["K"] * m["cin"] * m["cout"]
-        g["flops"] += 2.0 * P * m["cin"] * m["cout"]
+        kind, ms = m["kind"], e0.elapsed_time(e1)
+        if kind in ("gather_gemm", "gather_wgrad", "conv2d", "convt2d"):
+            key = (kind, m["cin"], m["cout"], m["K"])
+            P = m["P"] if "P" in m else pairs(m["nbr"])          # dense TMA convs: every tap of every output pixel
+            g = groups.setdefault(key, dict(ms=0.0, n=0, bytes=0.0, flops=0.0))
+            g["ms"] += ms; g["n"] += 1
+            g["bytes"] += 4.0 * (m["m_in"] * m["cin"] + m["m_out"] * m["cout"]) + 8.0 * P + 4.0 * m["K"] * m["cin"] * m["cout"]
+            g["flops"] += 2.0 * P * m["cin"] * m["cout"]
+            continue
+        # front end: algorithmic bytes per SURVEY 8d, in the layouts this implementation writes
+        if kind == "voxelize":
+            M = int(m["counts"][m["batch"]].item())
+            byt = 4.0 * m["n"] * m["c"] + M * (16.0 + 4.0 + (4.0 * m["c"] if m["want_mean"] else 0.0) +
+                                               (4.0 * m["max_pts"] * m["c"] if m["want_voxels"] else 0.0))
+            note = f"N={m['n']} M={M}"
+        elif kind == "rulebook_subm":
+            P = pairs(m["nbr"])
+            byt = 16.0 * m["m_in"] + 4.0 * m["m_out"] * m["K"]
+            stages[(m["m_out"], m["K"])] = dict(rows=m["m_out"], taps=m["K"], pairs=P)
+            note = f"M={m['m_out']} P={P}"
+        elif kind == "rulebook_strided_outputs":
+            mo = int(m["n_out"].item())
+            byt = 16.0 * m["m_in"] + 16.0 * mo
+            note = f"M_in={m['m_in']} M_out={mo}"
+        else:                                                    # rulebook_strided_tables
+            P = pairs(m["nbr"])
+            byt = 16.0 * (m["m_in"] + m["m_out"]) + 4.0 * m["K"] * (m["m_out"] + (m["m_in"] if m["both"] else 0))
+            note = f"M_in={m['m_in']} M_out={m['m_out']} P={P}"
+        f = front.setdefault(kind, dict(ms=0.0, n=0, bytes=0.0, last=""))
+        f["ms"] += ms; f["n"] += 1; f["bytes"] += byt; f["last"] = note
     gg_ms = sum(g["ms"] for g in groups.values())
+    front_end = [dict(kernel=k, bound="hbm", launches_per_step=f["n"] / a.steps, ms_per_step=f["ms"] / a.steps, avg_launch_us=1e3 * f["ms"] / f["n"],
+                      achieved=f["bytes"] / f["ms"] / 1e6, unit="GB/s", peak=hbm, frac=f["bytes"] / f["ms"] / 1e6 / hbm,
+                      share_of_step=f["ms"] / total_ms, last_launch=f["last"]) for k, f in sorted(front.items(), key=lambda kv: -kv[1]["ms"])]
     if os.environ.get("CPD_BENCH_GROUPS"):
         rows = sorted(((k, g) for k, g in groups.items()), key=lambda kv: -kv[1]["ms"])
         with open(os.environ["CPD_BENCH_GROUPS"], "w") as f:
@@ -294,6 +407,9 @@ def run_ours(a):
             for k, g in rows:
                 f.write(f"{k[0]} {k[1]} {k[2]} {k[3]} {g['n'] / a.steps:.1f} {g['ms'] / a.steps:.3f} {1e3 * g['ms'] / g['n']:.1f} "
                         f"{g['bytes'] / g['ms'] / 1e6:.0f} {g['flops'] / g['ms'] / 1e9:.1f}\n")
+            for fe in front_end:
+                f.write(f"{fe['kernel']} - - - {fe['launches_per_step']:.1f} {fe['ms_per_step']:.3f} {fe['avg_launch_us']:.1f} {fe['achieved']:.0f} - "
+                        f"({fe['last_launch']})\n")
     top_key, top = max(groups.items(), key=lambda kv: kv[1]["ms"])
     # The kernels run bf16x3 (3 bf16 tensor products per useful fp32-class product): the tensor roofline for USEFUL flops is
     # the measured bf16 peak / 3; a layer is HBM bound when its arithmetic intensity sits below that ridge.
@@ -314,7 +430,8 @@ def run_ours(a):
         if ent:
             traffic = ent["dram_bytes_per_launch"]
     others = []
-    for k, g in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])[1:4]:      # the next three layer shapes, for context
+    n_next = 3 if a.workload != "stress" else 12                 # stress: the whole C sweep
+    for k, g in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])[1:1 + n_next]:      # the next layer shapes, for context
         e = entry(g)
         others.append(dict(kernel=f"{k[0]} {k[1]}->{k[2]} K={k[3]}", bound=e["bound"], achieved=e["achieved"], unit=e["unit"],
                            frac=e["achieved"] / e["peak"], avg_launch_us=1e3 * g["ms"] / g["n"], share_of_step=g["ms"] / total_ms))
@@ -340,10 +457,11 @@ def run_ours(a):
                    "active_voxels_last_batch": int(enc.indices.shape[0])},
         "e2e": {"value": frames_total / (e2e_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "front_end": front_end,
+        "sparse_levels": sorted(stages.values(), key=lambda d: -d["rows"]),
     }
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(a, frames[:1], net if not train else None)
+        line["cpu_baseline"] = cpu_baseline(a, frames[:1], net if a.workload == "backbone_fwd" else None)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -360,6 +478,37 @@ def cpu_baseline(a, frames, net=None):
     cores = os.cpu_count() or 1
     O.set_threads(cores)
     torch.set_num_threads(cores)
+    # the reference's voxelizer is single-threaded per DataLoader worker: its 1-thread figure, on the first frame
+    tv = time.perf_counter()
+    for _ in range(3):
+        O.voxelize(frames[0], PC_RANGE, VOXEL_SIZE)
+    vox_1t = 3.0 / (time.perf_counter() - tv)
+    if a.workload == "stress":
+        rng = np.random.default_rng(3)
+        ws = {c: (rng.normal(0, 1, (c, 27, c)) * (27 * c) ** -0.5).astype(np.float32) for c in StressSweep.CH}
+        t0 = time.perf_counter()
+        n = 0
+        while True:
+            pts = frames[n % len(frames)]
+            v, c3, nn = O.voxelize(pts, PC_RANGE, VOXEL_SIZE)
+            O.mean_vfe(v, nn)
+            coords, shape = np.concatenate([np.zeros((len(c3), 1), np.int32), c3], 1), [41, 1504, 1504]
+            for st in range(4):
+                rb = O.rulebook_subm(coords, shape, 3)
+                for c in (StressSweep.CH if st == 0 else (StressSweep.CH[st],)):
+                    O.spconv_fwd(rng.normal(0, 1, (len(coords), c)).astype(np.float32), ws[c], None, rb)
+                if st < 3:
+                    rbd = O.rulebook_strided(coords, shape, 3, 2, StressSweep.PADS[st])
+                    coords, shape = rbd.out_coords, rbd.out_shape
+            rbo = O.rulebook_strided(coords, shape, (3, 1, 1), (2, 1, 1), 0)
+            O.dense(rng.normal(0, 1, (rbo.m_out, 128)).astype(np.float32), rbo.out_coords, 1, rbo.out_shape)
+            n += 1
+            dt = time.perf_counter() - t0
+            if dt > 10.0 or n >= 4:
+                break
+        return {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "port", "voxelizer_1thread_frames_per_s": vox_1t,
+                "sample": f"{n} frame(s) of the same sweep ({a.points} pts/frame): oracle/cpd_oracle.c voxelizer (1 thread, as the reference's) + "
+                          f"rulebooks + SubM convolutions + dense() (OpenMP, {cores} threads)"}
     if a.workload == "backbone_fwd":
         if net is None:
             net = make_net(torch.device("cpu"))
@@ -390,7 +539,7 @@ def cpu_baseline(a, frames, net=None):
             if dt > 12.0 or n >= 4:
                 break
         what = "fwd+bwd train step (bs=1, no optimizer update)"
-    return {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+    return {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "port", "voxelizer_1thread_frames_per_s": vox_1t,
             "sample": f"{n} frame(s) of the same workload ({a.points} pts/frame), {what}; oracle/cpd_oracle.c (OpenMP) + torch CPU "
                       f"for the dense head, {cores} threads"}
 

@@ -10,6 +10,26 @@ import torch
 from . import _lib
 
 
+# bench.py sets this to a list to time launches with CUDA events on the launching stream: entries are
+# (start_event, end_event, meta dict) -- gather-GEMM / wgrad / conv2d (meta holds the table or the pair count), voxelizer, rulebooks.
+PROFILE = None
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0
+
+
+def _prof_end(e0, **meta):
+    if e0 is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        PROFILE.append((e0, e1, meta))
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -72,10 +92,12 @@ def voxelize(points, frame_offsets, pc_range, voxel_size, max_pts=5, max_voxels=
     counts = torch.empty((batch + 1,), dtype=torch.int32, device=dev)
     wsb = L.cpd_voxelize_workspace_bytes(n, batch, max_pts, cap_rows)
     ws = _ws(wsb, dev)
+    e0 = _prof_begin()
     _lib.check(L.cpd_voxelize(_ptr(pts), n, c, offs, batch, rng, vs, int(max_pts), int(max_voxels), cap_rows,
                               _ptr(voxels), _ptr(coords), _ptr(num), _ptr(mean), _ptr(counts), _ptr(ws), wsb,
                               _stream()), "cpd_voxelize")
     out = dict(voxels=voxels, coords=coords, num=num, mean=mean, counts=counts)
+    _prof_end(e0, kind="voxelize", n=n, c=c, counts=counts, batch=batch, max_pts=max_pts, want_voxels=want_voxels, want_mean=want_mean)
     if sync:
         m = int(counts[batch].item())
         if m > cap_rows:
@@ -107,8 +129,10 @@ def subm_table(coords, shape, batch, ksize, hash_buf):
     K = ks[0] * ks[1] * ks[2]
     m = coords.shape[0]
     nbr = torch.empty((m, K), dtype=torch.int32, device=coords.device)
+    e0 = _prof_begin()
     _lib.check(L.cpd_rulebook_subm(_ptr(coords), m, _i32x3(shape), int(batch), ks, _ptr(hash_buf), hash_buf.numel(),
                                    _ptr(nbr), _stream()), "cpd_rulebook_subm")
+    _prof_end(e0, kind="rulebook_subm", m_in=m, m_out=m, K=K, nbr=nbr)
     return nbr
 
 
@@ -132,8 +156,10 @@ def strided_outputs(coords, shape, batch, ksize, stride, padding):
     cap = max(m * min(K, fan), 1)
     ocoords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
     n_out = torch.empty((1,), dtype=torch.int32, device=dev)
+    e0 = _prof_begin()
     _lib.check(L.cpd_rulebook_strided_outputs(_ptr(coords), m, sh, int(batch), ks, st, pd, oshape, cap, _ptr(ocoords),
                                               _ptr(n_out), _ptr(ws), wsb, _stream()), "cpd_rulebook_strided_outputs")
+    _prof_end(e0, kind="rulebook_strided_outputs", m_in=m, n_out=n_out, K=K, cells=int(wsb) * 8)
     mo = int(n_out.item())
     if mo > cap:
         raise _lib.CpdError("cpd_rulebook_strided_outputs: output capacity exceeded")
@@ -153,11 +179,13 @@ def strided_tables(in_coords, in_shape, in_hash, out_coords, out_shape, out_hash
     m_in, m_out = in_coords.shape[0], out_coords.shape[0]
     fwd = torch.empty((m_out, K), dtype=torch.int32, device=dev)
     bwd = torch.empty((m_in, K), dtype=torch.int32, device=dev) if want_bwd else None
+    e0 = _prof_begin()
     _lib.check(L.cpd_rulebook_strided_tables(_ptr(in_coords), m_in, _i32x3(in_shape), _ptr(in_hash), in_hash.numel(),
                                              _ptr(out_coords), m_out, _i32x3(out_shape),
                                              _ptr(out_hash) if want_bwd else None,
                                              out_hash.numel() if want_bwd else 0, int(batch), ks, st, pd,
                                              _ptr(fwd), _ptr(bwd), _stream()), "cpd_rulebook_strided_tables")
+    _prof_end(e0, kind="rulebook_strided_tables", m_in=m_in, m_out=m_out, K=K, nbr=fwd, both=want_bwd)
     return fwd, bwd
 
 
@@ -174,9 +202,6 @@ def conv2d_table(n, h, w, kh, kw, stride, pad, transposed, ho, wo, device):
 # ------------------------------------------------------------------------------------
 ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05 = 0, 1, 2
 
-# bench.py sets this to a list to time every gather-GEMM launch with CUDA events on the
-# launching stream: entries are (start_event, end_event, meta dict holding the nbr table).
-PROFILE = None
 
 
 def tc_gemm_ok(cin, K, cout):
@@ -298,21 +323,6 @@ def conv2d_ok(cin, k, cout):
     if key not in _CONV2D_OK:
         _CONV2D_OK[key] = bool(_lib.lib().cpd_conv2d_supported(key[0], key[1], key[1], key[2]))
     return _CONV2D_OK[key]
-
-
-def _prof_begin():
-    if PROFILE is None:
-        return None
-    e0 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    return e0
-
-
-def _prof_end(e0, **meta):
-    if e0 is not None:
-        e1 = torch.cuda.Event(enable_timing=True)
-        e1.record()
-        PROFILE.append((e0, e1, meta))
 
 
 def conv2d_fwd(x_split, n, h, w, weight, k, pad, bias=None, scale=None, shift=None, residual=None, relu=False, stats=None):

@@ -131,3 +131,36 @@ def synth_nms_boxes(n, seed, clusters=None):
     b[:, 6] = ch[which] + rng.normal(0, 0.08, n)
     scores = rng.uniform(0.1, 1.0, n).astype(np.float32)
     return b, scores
+
+
+def count_voxels(points, pc_range=PC_RANGE, voxel_size=VOXEL_SIZE):
+    """Number of distinct occupied cells of one sweep (same fp32 cell arithmetic as the voxelizer)."""
+    p = points[:, :3].astype(np.float32)
+    cell = np.floor((p - pc_range[:3]) / voxel_size).astype(np.int64)
+    grid = np.round((pc_range[3:] - pc_range[:3]) / voxel_size).astype(np.int64)
+    ok = ((cell >= 0) & (cell < grid)).all(1)
+    cell = cell[ok]
+    return int(np.unique((cell[:, 2] * grid[1] + cell[:, 1]) * grid[0] + cell[:, 0]).size)
+
+
+def synth_dense_scan(n_points=300000, seed=0, target_voxels=200000, tol=0.05):
+    """BASELINE configs[4], the dense-scene stress sweep: `n_points` points occupying target_voxels +- tol active voxels.
+    A sparse scene (few occluders) with strong elevation jitter spreads the rings over the far field; the ring spacing
+    exponent is then bisected until the voxel count lands in the window (the count depends on the random scene; a scene
+    whose occluders starve it is thinned out once).  Returns (points (n, 5) float32, voxel count)."""
+    best = None
+    for n_cars, n_walls in ((12, 2), (4, 0)):
+        lo, hi = 0.3, 2.4
+        for _ in range(8):
+            rp = 0.5 * (lo + hi)
+            pts = synth_scan(n_points, seed, rings=64, n_cars=n_cars, n_walls=n_walls, el_jitter=8e-3, ring_pow=rp)
+            m = count_voxels(pts)
+            if best is None or abs(m - target_voxels) < abs(best[1] - target_voxels):
+                best = (pts, m)
+            if abs(m - target_voxels) <= tol * target_voxels:
+                return best
+            if m < target_voxels:            # the count falls as the exponent grows (rings crowd towards the sensor)
+                hi = rp
+            else:
+                lo = rp
+    return best
