@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--points", type=int, default=160000, help="points per frame")
     ap.add_argument("--pool", type=int, default=2, help="distinct batches cycled through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the dense stack (BEV backbone + CenterHead convs) into CUDA graphs")
     ap.add_argument("--prefetch", action="store_true", help="run the input stage (voxelize + rulebooks) one step ahead on a side stream "
                                                             "(detector.prepare) instead of inline")
     a = ap.parse_args()
@@ -240,6 +241,8 @@ def run_ours(a):
         host_gt = [torch.from_numpy(np.stack(gts[k:k + a.batch])).pin_memory() for k in range(0, nfr, a.batch)]
         resident_gt = [g.to(dev) for g in host_gt]
         net = make_detector(dev)
+        if not a.no_graph:
+            net.capture_dense_graph(a.batch)                       # static-shape part of the step: forward + backward as CUDA graphs
         model = net
         if world > 1:
             model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local])
@@ -358,16 +361,16 @@ def run_ours(a):
     hbm, bf16, src = peaks()
     groups, front, pcache, stages = {}, {}, {}, {}
 
-    def pairs(t):
+    def pairs(t):                       # device scalar made by ops._prof_end
         if id(t) not in pcache:
-            pcache[id(t)] = int((t >= 0).sum().item())
+            pcache[id(t)] = int(t.item())
         return pcache[id(t)]
 
     for e0, e1, m in prof:
         kind, ms = m["kind"], e0.elapsed_time(e1)
         if kind in ("gather_gemm", "gather_wgrad", "conv2d", "convt2d"):
             key = (kind, m["cin"], m["cout"], m["K"])
-            P = m["P"] if "P" in m else pairs(m["nbr"])          # dense TMA convs: every tap of every output pixel
+            P = m["P"] if "P" in m else pairs(m["pairs"])        # dense TMA convs: every tap of every output pixel
             g = groups.setdefault(key, dict(ms=0.0, n=0, bytes=0.0, flops=0.0))
             g["ms"] += ms; g["n"] += 1
             g["bytes"] += 4.0 * (m["m_in"] * m["cin"] + m["m_out"] * m["cout"]) + 8.0 * P + 4.0 * m["K"] * m["cin"] * m["cout"]
@@ -380,7 +383,7 @@ def run_ours(a):
                                                (4.0 * m["max_pts"] * m["c"] if m["want_voxels"] else 0.0))
             note = f"N={m['n']} M={M}"
         elif kind == "rulebook_subm":
-            P = pairs(m["nbr"])
+            P = pairs(m["pairs"])
             byt = 16.0 * m["m_in"] + 4.0 * m["m_out"] * m["K"]
             stages[(m["m_out"], m["K"])] = dict(rows=m["m_out"], taps=m["K"], pairs=P)
             note = f"M={m['m_out']} P={P}"
@@ -389,7 +392,7 @@ def run_ours(a):
             byt = 16.0 * m["m_in"] + 16.0 * mo
             note = f"M_in={m['m_in']} M_out={mo}"
         else:                                                    # rulebook_strided_tables
-            P = pairs(m["nbr"])
+            P = pairs(m["pairs"])
             byt = 16.0 * (m["m_in"] + m["m_out"]) + 4.0 * m["K"] * (m["m_out"] + (m["m_in"] if m["both"] else 0))
             note = f"M_in={m['m_in']} M_out={m['m_out']} P={P}"
         f = front.setdefault(kind, dict(ms=0.0, n=0, bytes=0.0, last=""))
@@ -453,6 +456,8 @@ def run_ours(a):
                    "arithmetic": "fp32 in / fp32 out; convolution products on tcgen05 as bf16x3 (hi.hi + hi.lo + lo.hi, fp32 accumulate): "
                                  "2^-16 per product, not 2^-24",
                    "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write)",
+                   "cuda_graphs": ("dense stack (BEV backbone + CenterHead convolutions) forward and backward replayed as CUDA graphs"
+                                   if (train and not a.no_graph) else "none"),
                    "input_stage": "inline" if (a.no_prefetch or not train) else "prefetched one step ahead on a side stream (inside the timed region)",
                    "active_voxels_last_batch": int(enc.indices.shape[0])},
         "e2e": {"value": frames_total / (e2e_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,

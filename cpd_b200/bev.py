@@ -583,14 +583,17 @@ class CenterHead(nn.Module):
             rois[b, :m], scores[b, :m], labels[b, :m] = pred_dicts[b]["pred_boxes"], pred_dicts[b]["pred_scores"], pred_dicts[b]["pred_labels"]
         return rois, scores, labels
 
-    def forward(self, data_dict):
-        x = data_dict.get("st_features_2d_map")
-        if x is None:
-            x = DenseMap.from_nchw(data_dict["st_features_2d"])
-        x = self.shared_conv(x)
-        pred_dicts = [head(x) for head in self.heads_list]
+    def forward(self, data_dict, pred_dicts=None, fmap=None):
+        """pred_dicts / fmap: head outputs computed elsewhere (the CUDA-graphed dense stack) and the feature map size."""
+        if pred_dicts is None:
+            x = data_dict.get("st_features_2d_map")
+            if x is None:
+                x = DenseMap.from_nchw(data_dict["st_features_2d"])
+            x = self.shared_conv(x)
+            pred_dicts = [head(x) for head in self.heads_list]
+            fmap = (x.h, x.w)
         if self.training:
-            self.forward_ret_dict["target_dicts"] = self.assign_targets(data_dict["gt_boxes"], (x.h, x.w))
+            self.forward_ret_dict["target_dicts"] = self.assign_targets(data_dict["gt_boxes"], fmap)
         self.forward_ret_dict["pred_dicts"] = pred_dicts
         if not self.training or self.predict_boxes_when_training:
             boxes = self.generate_predicted_boxes(data_dict["batch_size"], pred_dicts)

@@ -23,13 +23,47 @@ MODEL_CFG = dict(
 )
 
 
+class DenseStack(nn.Module):
+    """BaseBEVBackbone + the CenterHead convolutions as ONE tensor -> tensors callable.  Its shapes are static (the BEV map is
+    always B x 188 x 188), so its forward and backward can each be captured into a CUDA graph
+    (CPDHotPathDetector.capture_dense_graph): ~27 conv + BatchNorm stages whose ~500 launches per step then cost two graph
+    launches of host time instead of Python enqueue work."""
+
+    def __init__(self, backbone_2d, dense_head, n, h, w):
+        super().__init__()
+        self.backbone_2d, self.dense_head = backbone_2d, dense_head
+        self.n, self.h, self.w = n, h, w
+        self.names = [[name for name in head.sep_head_dict] for head in dense_head.heads_list]
+
+    def forward(self, x_rows):
+        d = self.backbone_2d({"spatial_features": bev.DenseMap(x_rows, self.n, self.h, self.w)})
+        x = self.dense_head.shared_conv(d["st_features_2d_map"])
+        outs = []
+        for head, names in zip(self.dense_head.heads_list, self.names):
+            for name in names:
+                outs.append(getattr(head, name)(x).data)            # (n*h*w, c) rows
+        return tuple(outs)
+
+    def pred_dicts(self, outs):
+        """The list-of-dicts of NCHW views CenterHead.get_loss / generate_predicted_boxes expect."""
+        it, dicts = iter(outs), []
+        for names in self.names:
+            dicts.append({name: bev.DenseMap(next(it), self.n, self.h, self.w).nchw() for name in names})
+        return dicts
+
+
 class CPDHotPathDetector(nn.Module):
     """tools/cfgs/models/waymo_unsupervised/voxel_rcnn_cproto_center.yaml:12-80 without ROI_HEAD."""
 
     def __init__(self, model_cfg=None, pc_range=PC_RANGE, voxel_size=VOXEL_SIZE, num_point_features=5, max_pts=5,
                  max_voxels=1000000, class_names=("Vehicle", "Pedestrian", "Cyclist"), res_backbone=True,
-                 predict_boxes_when_training=True):
+                 predict_boxes_when_training=True, device_point_pipeline=False):
         super().__init__()
+        # device_point_pipeline: run the dataset-side point pipeline (range mask + train-time shuffle,
+        # data_processor.py:77-126) on the device, after the H2D copy of the RAW sweep (SURVEY 8f-2)
+        self.device_point_pipeline = device_point_pipeline
+        self._shuffle_gen = None
+        self._dense_graph = None
         self._side = None
         self._held = (None, None)
         cfg = model_cfg or MODEL_CFG
@@ -49,6 +83,11 @@ class CPDHotPathDetector(nn.Module):
 
     def _voxelize(self, frames, device):
         frames = [f if f.is_cuda else f.to(device, non_blocking=True) for f in frames]
+        if self.device_point_pipeline:
+            if self._shuffle_gen is None:
+                self._shuffle_gen = torch.Generator(device=device)
+                self._shuffle_gen.manual_seed(0)
+            frames = [voxel.mask_and_shuffle_points(f, self.pc_range, self._shuffle_gen, shuffle=self.training)[0] for f in frames]
         return voxel.voxelize_batch(frames, self.pc_range, self.voxel_size, self.max_pts, self.max_voxels)
 
     def _input_stage(self, batch, device, plan):
@@ -68,6 +107,21 @@ class CPDHotPathDetector(nn.Module):
             if mm:
                 bd["tower_plan1"] = self.backbone_3d.plan_tower("_2", bd["voxel_coords1"], bs, False)
         return bd
+
+    def capture_dense_graph(self, batch_size):
+        """Capture forward and backward of the dense stack (BEV backbone + CenterHead convs, training mode) into CUDA graphs
+        (torch.cuda.make_graphed_callables: warm-up on a side stream, then one capture each).  Call once, in training mode,
+        before wrapping the detector in DistributedDataParallel.  BatchNorm running statistics touched by the warm-up
+        iterations are restored afterwards."""
+        assert self.training, "the captured graphs hold the training-mode (batch statistics) kernels"
+        dev = next(self.parameters()).device
+        stack = DenseStack(self.backbone_2d, self.dense_head, batch_size, self.grid_size[1] // 8, self.grid_size[0] // 8)
+        saved = {k: v.clone() for k, v in stack.state_dict().items() if "running_" in k or "num_batches" in k}
+        sample = (torch.randn(batch_size * stack.h * stack.w, self.backbone_2d.blocks[0][1].in_channels, device=dev) *
+                  (torch.rand(batch_size * stack.h * stack.w, 1, device=dev) < 0.1)).requires_grad_(True)
+        graphed = torch.cuda.make_graphed_callables(stack, (sample,), allow_unused_input=True)
+        stack.load_state_dict(saved, strict=False)
+        self._dense_graph = (stack, graphed, batch_size)
 
     def prepare(self, batch):
         """Run the input stage of a step on a side stream (the device-side analogue of a prefetching DataLoader):
@@ -107,8 +161,12 @@ class CPDHotPathDetector(nn.Module):
         sf = bd["spatial_features"]                       # (B, 256, H, W) logical NCHW over NHWC memory
         n, c, h, w = sf.shape
         bd["spatial_features"] = bev.DenseMap(sf.permute(0, 2, 3, 1).reshape(n * h * w, c), n, h, w)
-        bd = self.backbone_2d(bd)
-        bd = self.dense_head(bd)
+        if self._dense_graph is not None and self.training and n == self._dense_graph[2] and torch.is_grad_enabled():
+            stack, graphed, _ = self._dense_graph            # static shapes: forward + backward replay as CUDA graphs
+            bd = self.dense_head(bd, pred_dicts=stack.pred_dicts(graphed(bd["spatial_features"].data)), fmap=(h, w))
+        else:
+            bd = self.backbone_2d(bd)
+            bd = self.dense_head(bd)
         self.last_batch_dict = bd
         if self.training:
             loss, tb = self.dense_head.get_loss()

@@ -27,6 +27,13 @@ def _prof_end(e0, **meta):
     if e0 is not None:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
+        nbr = meta.pop("nbr", None)
+        if nbr is not None:                  # keep the PAIR COUNT (a device scalar, computed after the timed bracket), not the table:
+            p = getattr(nbr, "_cpd_pairs", None)      # holding every table of every step would pin gigabytes in the allocator
+            if p is None:
+                p = (nbr >= 0).sum()
+                nbr._cpd_pairs = p
+            meta["pairs"] = p
         PROFILE.append((e0, e1, meta))
 
 
@@ -269,19 +276,14 @@ def gather_gemm(x, w, nbr, bias=None, scale=None, shift=None, residual=None, rel
     residual = _f32c(residual) if residual is not None else None
     wsb = L.cpd_gather_gemm_workspace_bytes(x.shape[0], m_out, cin, K, cout, algo, int(x_split is not None))
     ws = _ws(wsb, x.device) if wsb else None
-    if PROFILE is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+    e0 = _prof_begin()
     assert tile_masks is None or tile_masks.numel() == (m_out + 127) // 128
     assert out_rows is None or (out_rows.dtype == torch.int32 and out_rows.numel() == m_out and out_rows.is_contiguous())
     _lib.check(L.cpd_gather_gemm(_ptr(x), _ptr(x_split), x.shape[0], cin, _ptr(w), K, cout, _ptr(nbr), _ptr(tile_masks), _ptr(out_rows),
                                  m_out, _ptr(bias),
                                  _ptr(scale), _ptr(shift), _ptr(residual), int(bool(relu)), _ptr(stats), _ptr(y), int(algo),
                                  _ptr(ws), wsb, _stream()), "cpd_gather_gemm")
-    if PROFILE is not None:
-        e1.record()
-        PROFILE.append((e0, e1, dict(kind="gather_gemm", m_in=x.shape[0], m_out=m_out, cin=cin, cout=cout, K=K, nbr=nbr,
-                                     residual=residual is not None)))
+    _prof_end(e0, kind="gather_gemm", m_in=x.shape[0], m_out=m_out, cin=cin, cout=cout, K=K, nbr=nbr, residual=residual is not None)
     return y
 
 
@@ -298,16 +300,11 @@ def gather_wgrad(x, dy, nbr, want_bias=False, algo=ALGO_AUTO, tap_major=False, x
     wsb = 0 if algo == ALGO_SIMT else L.cpd_gather_wgrad_workspace_bytes(x.shape[0], dy.shape[0], cin, K, cout,
                                                                           int(x_split is not None), int(dy_split is not None))
     ws = _ws(wsb, x.device) if wsb else None
-    if PROFILE is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+    e0 = _prof_begin()
     _lib.check(L.cpd_gather_wgrad(_ptr(x), _ptr(x_split), x.shape[0], cin, _ptr(dy), _ptr(dy_split), dy.shape[0], cout, _ptr(nbr),
                                   int(bool(tap_major)), K, _ptr(dw), _ptr(db), int(algo), _ptr(ws), wsb, _stream()),
                "cpd_gather_wgrad")
-    if PROFILE is not None:
-        e1.record()
-        PROFILE.append((e0, e1, dict(kind="gather_wgrad", m_in=x.shape[0], m_out=dy.shape[0], cin=cin, cout=cout, K=K, nbr=nbr,
-                                     residual=False)))
+    _prof_end(e0, kind="gather_wgrad", m_in=x.shape[0], m_out=dy.shape[0], cin=cin, cout=cout, K=K, nbr=nbr, residual=False)
     return dw, db
 
 

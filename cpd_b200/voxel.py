@@ -99,6 +99,27 @@ def gather_features_by_pc_voxel_id(seg_res_features, pc_voxel_id, invalid_value=
     return res
 
 
+def mask_and_shuffle_points(points, pc_range, generator=None, shuffle=True):
+    """DataProcessor.mask_points_and_boxes_outside_range + shuffle_points (cpd/datasets/processor/data_processor.py:77-126,
+    cpd/utils/common_utils.py:60-63) for one raw sweep ALREADY ON THE DEVICE: keep the points whose x, y lie inside the
+    range (inclusive at both ends, z unchecked -- exactly the reference's mask), then apply a random permutation.
+    No host sync: the mask is applied by a stable partition (rejected points are moved behind the kept ones and carry NaN
+    coordinates, which the voxelizer drops like any out-of-range point), so the tensor keeps its static size.
+    Returns (points (n, C), number of kept points as a 0-d device tensor)."""
+    x, y = points[:, 0], points[:, 1]
+    keep = (x >= pc_range[0]) & (x <= pc_range[3]) & (y >= pc_range[1]) & (y <= pc_range[4])
+    n = points.shape[0]
+    if shuffle:
+        perm = torch.randperm(n, device=points.device, generator=generator)
+        points, keep = points.index_select(0, perm), keep.index_select(0, perm)
+    order = torch.sort((~keep).to(torch.uint8), stable=True)[1]          # kept points first, order preserved
+    out = points.index_select(0, order)
+    n_keep = keep.sum()
+    tail = torch.arange(n, device=points.device) >= n_keep
+    out = torch.where(tail[:, None], torch.full_like(out, float("nan")), out)
+    return out, n_keep
+
+
 def voxelize_batch(points_list, pc_range, voxel_size, max_pts=5, max_voxels=1000000, want_voxels=False):
     """list of (n_i, C) CUDA tensors (or one concatenated tensor + offsets) -> batch_dict entries
     ``voxels``, ``voxel_coords`` (float like load_data_to_gpu would make them is NOT done: int32
