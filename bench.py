@@ -318,6 +318,8 @@ def run_ours(a):
             evs.append((e0, e1))
         barrier()
         launches = _lib.launch_count() - l0
+        if train and not a.no_graph:            # kernels replayed from the captured graphs do not pass through the library's counter
+            launches += net.dense_graph_launches * a.steps
         total_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
         # ---- roofline pass: the same K steps again with CUDA events around every gather-GEMM / wgrad launch
         #      (per-launch events perturb the step, so `value` above comes from the clean pass) ----
@@ -335,6 +337,8 @@ def run_ours(a):
         prof, ops.PROFILE = ops.PROFILE, None
         prof_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs_p)
         # ---- end-to-end: host (pinned) inputs in, result scalar out, every step ----
+        for i in range(a.warmup):                # the host path has its own first-use costs (staging buffers of the H2D copies in the
+            run_host(i)                          # stream's allocator pool): W untimed steps of it, like the resident leg
         evs2 = []
         d2h = 0
         barrier()

@@ -46,6 +46,9 @@ SIGNATURES = {
     "cpd_convt2d_fwd": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "cpd_sparse_to_dense": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp]),
     "cpd_sparse_to_dense_bwd": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp]),
+    "cpd_voxel_query": (_i32, [_vp, _vp, _i64, _vp, _vp, _sz, _vp, _vp, _i32, _vp, _f, _i32, _vp, _vp, _vp]),
+    "cpd_group_points": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "cpd_group_points_bwd": (_i32, [_vp, _vp, _i64, _i32, _i32, _i64, _vp, _vp]),
     "cpd_overlap_bev": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp]),
     "cpd_iou_bev": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp]),
     "cpd_nms_workspace_bytes": (_sz, [_i32]),

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libcpd_b200.so")
-SOURCES = ["api.cu", "voxelize.cu", "rulebook.cu", "spconv_simt.cu", "split.cu", "spconv_tc.cu", "conv2d_api.cu", "wgrad_tc.cu", "batchnorm.cu", "nms.cu"]
+SOURCES = ["api.cu", "voxelize.cu", "rulebook.cu", "spconv_simt.cu", "split.cu", "spconv_tc.cu", "conv2d_api.cu", "wgrad_tc.cu", "batchnorm.cu", "nms.cu", "roipool.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -28,7 +28,6 @@ _OUT_OF_SCOPE_EXTENSIONS = (
     "cpd.ops.roiaware_pool3d.roiaware_pool3d_cuda",
     "cpd.ops.roipoint_pool3d.roipoint_pool3d_cuda",
     "cpd.ops.pointnet2.pointnet2_batch.pointnet2_batch_cuda",
-    "cpd.ops.pointnet2.pointnet2_stack.pointnet2_stack_cuda",
     "cpd.ops.votr_ops.votr_ops_cuda",
     "cpd.ops.dcn.deform_conv_cuda",
 )
@@ -104,6 +103,9 @@ def install_reference(root):
     from .. import iou3d_nms_cuda
     _register("cpd.ops.iou3d_nms.iou3d_nms_cuda", iou3d_nms_cuda)
     sys.modules["cpd.ops.iou3d_nms"].iou3d_nms_cuda = iou3d_nms_cuda
+    from .. import pointnet2_stack_cuda           # voxel query + grouping of the RoI grid pooling
+    _register("cpd.ops.pointnet2.pointnet2_stack.pointnet2_stack_cuda", pointnet2_stack_cuda)
+    sys.modules["cpd.ops.pointnet2.pointnet2_stack"].pointnet2_stack_cuda = pointnet2_stack_cuda
     for name in _OUT_OF_SCOPE_EXTENSIONS:
         stub = _register(name, _Unavailable(name))
         parent, _, leaf = name.rpartition(".")

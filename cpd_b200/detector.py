@@ -64,6 +64,7 @@ class CPDHotPathDetector(nn.Module):
         self.device_point_pipeline = device_point_pipeline
         self._shuffle_gen = None
         self._dense_graph = None
+        self.dense_graph_launches = 0           # libcpd_b200 kernels replayed per step by the captured graphs
         self._side = None
         self._held = (None, None)
         cfg = model_cfg or MODEL_CFG
@@ -114,7 +115,16 @@ class CPDHotPathDetector(nn.Module):
         before wrapping the detector in DistributedDataParallel.  BatchNorm running statistics touched by the warm-up
         iterations are restored afterwards."""
         assert self.training, "the captured graphs hold the training-mode (batch statistics) kernels"
+        import gc
+        from . import _lib
+        # autograd graphs of earlier steps keep AccumulateGrad nodes bound to the stream they ran on; the engine would
+        # synchronise the capturing stream with it (and invalidate the capture): drop every reference this module holds
+        self.last_batch_dict = None
+        self.dense_head.forward_ret_dict.clear()
+        self._held = (None, None)
+        gc.collect()
         dev = next(self.parameters()).device
+        l0 = _lib.launch_count()
         stack = DenseStack(self.backbone_2d, self.dense_head, batch_size, self.grid_size[1] // 8, self.grid_size[0] // 8)
         saved = {k: v.clone() for k, v in stack.state_dict().items() if "running_" in k or "num_batches" in k}
         sample = (torch.randn(batch_size * stack.h * stack.w, self.backbone_2d.blocks[0][1].in_channels, device=dev) *
@@ -122,6 +132,8 @@ class CPDHotPathDetector(nn.Module):
         graphed = torch.cuda.make_graphed_callables(stack, (sample,), allow_unused_input=True)
         stack.load_state_dict(saved, strict=False)
         self._dense_graph = (stack, graphed, batch_size)
+        # kernels inside the two graphs: make_graphed_callables ran 3 warm-up iterations + 1 captured forward + backward
+        self.dense_graph_launches = (_lib.launch_count() - l0) // 4
 
     def prepare(self, batch):
         """Run the input stage of a step on a side stream (the device-side analogue of a prefetching DataLoader):

@@ -502,3 +502,47 @@ def bn_train_bwd(x, y, dy, mean_invstd, gamma, relu, want_residual, want_split=F
     _lib.check(L.cpd_bn_train_bwd(_ptr(x), _ptr(y), _ptr(dy), m, c, _ptr(mean_invstd), _ptr(gamma), int(bool(relu)), _ptr(dx),
                                   _ptr(dxs), _ptr(dres), _ptr(gb), _stream()), "cpd_bn_train_bwd")
     return dx, dres, gb[1], gb[0], dxs
+
+
+# ------------------------------------------------------------------------------------
+# RoI grid pooling primitives (voxel query + point grouping)
+# ------------------------------------------------------------------------------------
+def voxel_query(new_xyz, new_coords, xyz, shape, batch, ranges, radius, nsample, hash_buf=None, dense_map=None):
+    """-> (idx (m, nsample) int32 global rows, empty (m,) bool).  new_coords (m, 4) int32 [b, z, y, x].  Pass the level's
+    coordinate hash (build_hash / SparseConvTensor.coord_hash()) or the reference's dense (B, Z, Y, X) int32 map."""
+    _need_cuda(new_xyz, new_coords, xyz)
+    L = _lib.lib()
+    new_xyz, xyz = _f32c(new_xyz), _f32c(xyz)
+    new_coords = new_coords if (new_coords.dtype == torch.int32 and new_coords.is_contiguous()) else new_coords.int().contiguous()
+    m = new_xyz.shape[0]
+    idx = torch.empty((m, nsample), dtype=torch.int32, device=xyz.device)
+    empty = torch.empty((m,), dtype=torch.uint8, device=xyz.device)
+    assert (hash_buf is None) != (dense_map is None)
+    if dense_map is not None:
+        assert dense_map.dtype == torch.int32 and dense_map.is_contiguous()
+    _lib.check(L.cpd_voxel_query(_ptr(new_xyz), _ptr(new_coords), m, _ptr(xyz), _ptr(hash_buf), hash_buf.numel() if hash_buf is not None else 0,
+                                 _ptr(dense_map), _i32x3(shape), int(batch), _i32x3(ranges), float(radius), int(nsample), _ptr(idx), _ptr(empty),
+                                 _stream()), "cpd_voxel_query")
+    return idx, empty.bool()
+
+
+def group_points(features, idx):
+    """(n, c), (m, nsample) int32 global rows -> (m, c, nsample)."""
+    _need_cuda(features, idx)
+    L = _lib.lib()
+    features = _f32c(features)
+    m, ns = idx.shape
+    c = features.shape[1]
+    out = torch.empty((m, c, ns), dtype=torch.float32, device=features.device)
+    _lib.check(L.cpd_group_points(_ptr(features), _ptr(idx), m, c, ns, _ptr(out), _stream()), "cpd_group_points")
+    return out
+
+
+def group_points_bwd(grad_out, idx, n):
+    _need_cuda(grad_out, idx)
+    L = _lib.lib()
+    grad_out = _f32c(grad_out)
+    m, c, ns = grad_out.shape
+    g = torch.empty((n, c), dtype=torch.float32, device=grad_out.device)
+    _lib.check(L.cpd_group_points_bwd(_ptr(grad_out), _ptr(idx), m, c, ns, n, _ptr(g), _stream()), "cpd_group_points_bwd")
+    return g

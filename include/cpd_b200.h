@@ -256,6 +256,28 @@ CPD_API int32_t cpd_sparse_to_dense_bwd(const float *dout, const int32_t *coords
                                 cpd_stream_t stream);
 
 /* ---------------------------------------------------------------------------------
+ * RoI grid pooling primitives of VoxelRCNN[Proto]Head.  Replace
+ * cpd/ops/pointnet2/pointnet2_stack/src/voxel_query_gpu.cu:10-89 (voxel_query_wrapper) and
+ * group_points_gpu.cu:15-125 (group_points[_grad]_wrapper), as driven by
+ * cpd/models/roi_heads/voxel_rcnn_head.py:186-273 and pointnet2_stack/voxel_query_utils.py:12-110.
+ * The voxel -> row lookup probes the level's coordinate hash (cpd_coord_hash_build) instead of the dense
+ * (B, Z, Y, X) int32 map the reference scatters per scale per call (cpd/utils/spconv_utils.py:4-21); passing that dense
+ * map instead of the hash keeps the reference's own Python running on the shim.
+ * new_xyz (m, 3) query points; new_coords (m, 4) int32 [b, z, y, x] their cells at this scale; xyz (n, 3) voxel centres;
+ * idx (m, nsample) int32 GLOBAL rows (the reference returns the same and rebases per batch in Python); empty (m,) uint8.
+ * Scan order, radius test and fill rule are the reference's: results are bit-identical.
+ * --------------------------------------------------------------------------------- */
+CPD_API int32_t cpd_voxel_query(const float *new_xyz, const int32_t *new_coords, int64_t m, const float *xyz, const void *hash,
+                        size_t hash_bytes, const int32_t *dense_map, const int32_t *shape3_host, int32_t batch,
+                        const int32_t *range3_host, float radius, int32_t nsample, int32_t *idx, uint8_t *empty,
+                        cpd_stream_t stream);
+/* out (m, c, nsample) = features[idx[m, s], c]; the _bwd entry overwrites grad_features (n, c) with the scattered sum. */
+CPD_API int32_t cpd_group_points(const float *features, const int32_t *idx, int64_t m, int32_t c, int32_t nsample, float *out,
+                         cpd_stream_t stream);
+CPD_API int32_t cpd_group_points_bwd(const float *grad_out, const int32_t *idx, int64_t m, int32_t c, int32_t nsample, int64_t n,
+                             float *grad_features, cpd_stream_t stream);
+
+/* ---------------------------------------------------------------------------------
  * iou3d_nms.  Replace cpd/ops/iou3d_nms/src/iou3d_nms.h:9-12 (boxes_overlap_bev_gpu,
  * boxes_iou_bev_gpu, nms_gpu, nms_normal_gpu).  boxes: (n,7) fp32
  * [x,y,z,dx,dy,dz,heading].  NMS expects rows sorted by descending score, like the

@@ -204,3 +204,9 @@ def ref_gpu_lib():
     """The reference's iou3d_nms_kernel.cu compiled unmodified for sm_100a, or None."""
     path = os.path.join(_HERE, "_ref", "libiou3d_ref_gpu.so")
     return C.CDLL(path) if os.path.exists(path) else None
+
+
+def ref_pointnet2_lib():
+    """The reference's voxel_query_gpu.cu + group_points_gpu.cu compiled unmodified for sm_100a, or None."""
+    path = os.path.join(_HERE, "_ref", "libpointnet2_ref_gpu.so")
+    return C.CDLL(path) if os.path.exists(path) else None
