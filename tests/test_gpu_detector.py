@@ -209,28 +209,50 @@ def test_prepared_input_stage_matches_inline(cuda):
 
 def test_dense_stack_cuda_graph_matches_eager(cuda):
     """capture_dense_graph: the BEV backbone + CenterHead convolutions replayed as CUDA graphs give the same loss and the same
-    parameter gradients as the eager path (same kernels, same order; only split-K atomics reorder)."""
+    parameter gradients as the eager path (same kernels, same order; only split-K / statistics atomics reorder).
+    Two EAGER runs of this randomly initialised 50-BatchNorm-stage network already differ by ~2 % (median over parameters,
+    tools/diag_graph.py) because fp32 atomics reorder and BatchNorm backward cancels most of every gradient -- biases in front
+    of a BatchNorm have an exactly-zero true gradient, i.e. pure rounding noise -- so the bound for the graph replay is the
+    measured eager-vs-eager spread of each parameter, not a fixed relative tolerance."""
     from cpd_b200 import detector
     torch.manual_seed(0)
     det = detector.CPDHotPathDetector().to(cuda).train()
     batch = _batch(cuda, 2, 20000, seed0=70)
     state = {k: v.clone() for k, v in det.state_dict().items()}
-    loss0, _ = det(batch)
-    loss0.backward()
-    g0 = {n: p.grad.clone() for n, p in det.named_parameters()}
-    det.load_state_dict(state)                                   # BatchNorm running statistics back to the start
+
+    def run():
+        det.load_state_dict(state)                               # BatchNorm running statistics back to the start
+        det.zero_grad(set_to_none=True)
+        loss, _ = det(batch)
+        loss.backward()
+        g = {n: p.grad.clone() for n, p in det.named_parameters()}
+        lv = float(loss.detach())
+        del loss                                                 # (no autograd graph of an earlier step may stay alive across the capture)
+        return lv, g
+
+    l0, g0 = run()
+    noise = {n: torch.zeros((), device=cuda) for n in g0}
+    for _ in range(2):
+        li, gi = run()
+        assert abs(li - l0) <= 1e-5 * max(1.0, abs(l0))
+        for n in g0:
+            noise[n] = torch.maximum(noise[n], (gi[n] - g0[n]).abs().max())
+    det.load_state_dict(state)
     det.zero_grad(set_to_none=True)
-    l0 = float(loss0.detach())
-    del loss0                                                    # (no autograd graph of an earlier step may stay alive across the capture)
     det.capture_dense_graph(2)
     assert det.dense_graph_launches > 100
     assert all(torch.equal(v, det.state_dict()[k]) for k, v in state.items()), "capture must not change the model state"
     for rep in range(2):                                         # replay twice: static buffers are reused
-        det.load_state_dict(state)
-        det.zero_grad(set_to_none=True)
-        loss1, _ = det(batch)
-        loss1.backward()
-        assert abs(float(loss1.detach()) - l0) <= 1e-5 * max(1.0, abs(l0)), (rep, l0, float(loss1.detach()))
-        for n, p in det.named_parameters():
-            ref = g0[n]
-            assert p.grad is not None and float((p.grad - ref).abs().max()) <= 5e-3 * max(1e-6, float(ref.abs().max())) + 1e-7, (rep, n)   # atomics order x the conditioning of ~50 BN stages
+        l1, g1 = run()
+        assert abs(l1 - l0) <= 1e-5 * max(1.0, abs(l0)), (rep, l0, l1)
+        bad = []
+        for n, ref in g0.items():
+            assert g1[n] is not None and torch.isfinite(g1[n]).all(), n
+            d = float((g1[n] - ref).abs().max())
+            if d > 4.0 * float(noise[n]) + 1e-3 * float(ref.abs().max()) + 1e-7:
+                bad.append((n, d, float(noise[n]), float(ref.abs().max())))
+        # the graphed part itself (dense stack weights: short, well-conditioned gradient paths) must agree tightly
+        assert not bad, (rep, bad[:5])
+    for n, ref in g0.items():
+        if (n.startswith("dense_head") or n.startswith("backbone_2d")) and n.endswith("weight") and ref.dim() > 1:
+            assert float((g1[n] - ref).abs().max()) <= 2e-2 * float(ref.abs().max()) + 4.0 * float(noise[n]), n
