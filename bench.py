@@ -37,12 +37,13 @@ def parse():
     ap.add_argument("--pool", type=int, default=2, help="distinct batches cycled through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the dense stack (BEV backbone + CenterHead convs) into CUDA graphs")
-    ap.add_argument("--prefetch", action="store_true", help="run the input stage (voxelize + rulebooks) one step ahead on a side stream "
-                                                            "(detector.prepare) instead of inline")
+    ap.add_argument("--prefetch", action="store_true", help="(default) run the input stage (voxelize + rulebooks) one step ahead on a side "
+                                                            "stream (detector.prepare), like a prefetching DataLoader")
+    ap.add_argument("--no-prefetch", action="store_true", help="run the input stage inline at the start of every forward")
     a = ap.parse_args()
     if a.workload == "stress" and a.points == 160000:
         a.points = 300000                      # BASELINE configs[4]: 300k points / 200k active voxels per frame
-    a.no_prefetch = not a.prefetch
+    a.prefetch = not a.no_prefetch             # measured on one B200: 47.1 ms/step prefetched vs 52.0 inline (profiles/r2_*)
     if a.prefetch:
         # the side stream has its own caching-allocator pool; with the default allocator its growth (cudaMalloc per new
         # segment size) made the first ~10 steps 1.5-2.5x slower -- expandable segments removed that (measured)
@@ -320,7 +321,8 @@ def run_ours(a):
         launches = _lib.launch_count() - l0
         if train and not a.no_graph:            # kernels replayed from the captured graphs do not pass through the library's counter
             launches += net.dense_graph_launches * a.steps
-        total_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+        step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+        total_ms = sum(step_ms)
         # ---- roofline pass: the same K steps again with CUDA events around every gather-GEMM / wgrad launch
         #      (per-launch events perturb the step, so `value` above comes from the clean pass) ----
         ops.PROFILE = []
@@ -453,7 +455,8 @@ def run_ours(a):
 
     line = {
         "metric": METRIC, "value": frames_total / (total_ms / 1e3), "unit": "frames/s", "n_gpus": world,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "ms_steps_rank0": [round(v, 2) for v in step_ms],
+        "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "arith": "bf16x3", "data": "synthetic",
         "config": {"workload": workload_name(a), "frames_per_step_per_gpu": a.batch, "points_per_frame": a.points,
                    "voxel_size": [0.1, 0.1, 0.15], "grid": [1504, 1504, 40], "parallelism": f"dp{world}",

@@ -100,6 +100,7 @@ struct TcArgs {
     long long m_out;
     int cin, K, cout, relu;
     int cin_shift;              // log2(cin) when cin is a power of two (every CPD layer), else -1
+    int l2_hints;               // gathers with L2 evict_last, table slices with evict_first (CPD_L2_HINTS, default on)
 };
 
 // DENSE variant (cpd_conv2d_fwd / cpd_conv2d_dgrad: the dense BEV convolutions, stride 1): the rows of an output tile are a
@@ -318,15 +319,16 @@ __global__ void __launch_bounds__(DENSE ? NTHREADS_DENSE : NTHREADS_SP, 1) gathe
 #pragma unroll
         for (int j = 0; j < A_V; ++j) soff[j] = swz(r_base + RSTEP * j, c);
         const uint32_t tiles_u32 = smem_u32(tiles);
-        const size_t row_bytes = (size_t)a.cin * 4;                // image row = hi(cin) | lo(cin) bf16
+        const uint32_t row_bytes = (uint32_t)a.cin * 4;            // image row = hi(cin) | lo(cin) bf16
         const uint32_t lo_off = (uint32_t)a.cin * 2;
+        const uint32_t tab_stride = (uint32_t)(RSTEP * a.K * 4);   // bytes between the table rows of this thread's chunks
+        const uint32_t tab0 = smem_u32(nbr_s) + (uint32_t)(r_base * a.K * 4);
+        const uint64_t pol_keep = l2_policy_evict_last();          // a feature row is gathered by ~K/2 output rows: keep it in L2
         int g = 0, ti = 0;                            // k-blocks issued so far (all tiles), tiles started
         for (long long t = fetch_tile(0); t < total_tiles; t = fetch_tile(++ti)) {
-            const long long row0 = (t / ntn) * BM;
             const int tb = ti & 1;
             mbar_wait(tblf0 + 8 * tb, (ti >> 1) & 1);                              // this tile's slice of the neighbour table has landed
-            const int32_t *tab = nbr_s + tb * tbl_ints + r_base * a.K;
-            int rows_left = (int)min((long long)BM, a.m_out - row0) - r_base;     // rows r_base + RSTEP j < rows of the tile
+            const uint32_t tab = tab0 + (uint32_t)(tb * tbl_ints * 4);            // (rows past m_out carry -1: see load_table)
             for (int kb = 0; kb < n_kb; ++kb) {
                 if (!kb_active(kb)) continue;
                 const int s = g % STAGES;
@@ -335,16 +337,33 @@ __global__ void __launch_bounds__(DENSE ? NTHREADS_DENSE : NTHREADS_SP, 1) gathe
                 int k, ch;                              // (a runtime integer division here cost 12 % of the kernel's instructions)
                 if (a.cin_shift >= 0) { k = f >> a.cin_shift; ch = f & (a.cin - 1); }
                 else { k = f / a.cin; ch = f - k * a.cin; }
-                const bool k_ok = k < a.K;
-                const uint32_t dst = tiles_u32 + (uint32_t)(s * STAGE);
-                const uint8_t *col = a.xs + (size_t)ch * 2;
+                // chunks past the last tap (f >= K cin, last k-block only) meet zero weights (weight_split_kernel) or lie beyond
+                // the K steps the MMA warp issues: any FINITE data will do there, so they re-read tap K-1 instead of branching
+                k = min(k, a.K - 1);
+                // The whole producer loop is latency-bound per warp (ncu: one generic table load -> address -> copy chain per row,
+                // serialised by the copies' "memory" clobbers): fetch the A_V indices FIRST, back to back, then issue the copies.
+                int32_t idx[A_V];
+                const uint32_t tk = tab + (uint32_t)(k * 4);
 #pragma unroll
-                for (int j = 0; j < A_V; ++j) {
-                    const int32_t idx = (k_ok && RSTEP * j < rows_left) ? tab[RSTEP * j * a.K + k] : -1;
-                    const uint8_t *src = col + (size_t)(idx >= 0 ? idx : 0) * row_bytes;
-                    const uint32_t sz = idx >= 0 ? 16u : 0u;             // 0 -> the copy writes 16 zero bytes
-                    cp_async16(dst + soff[j], src, sz);
-                    cp_async16(dst + A_BYTES + soff[j], src + lo_off, sz);
+                for (int j = 0; j < A_V; ++j) idx[j] = lds_i32(tk + (uint32_t)j * tab_stride);
+                const uint32_t dst = tiles_u32 + (uint32_t)(s * STAGE);
+                const uint8_t *col_hi = a.xs + (size_t)ch * 2, *col_lo = col_hi + lo_off;
+                if (a.l2_hints) {
+#pragma unroll
+                    for (int j = 0; j < A_V; ++j) {
+                        const uint32_t sz = idx[j] >= 0 ? 16u : 0u;      // 0 -> the copy writes 16 zero bytes
+                        const uint64_t off = (uint64_t)(uint32_t)max(idx[j], 0) * row_bytes;
+                        cp_async16_hint(dst + soff[j], col_hi + off, sz, pol_keep);
+                        cp_async16_hint(dst + A_BYTES + soff[j], col_lo + off, sz, pol_keep);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < A_V; ++j) {
+                        const uint32_t sz = idx[j] >= 0 ? 16u : 0u;
+                        const uint64_t off = (uint64_t)(uint32_t)max(idx[j], 0) * row_bytes;
+                        cp_async16(dst + soff[j], col_hi + off, sz);
+                        cp_async16(dst + A_BYTES + soff[j], col_lo + off, sz);
+                    }
                 }
                 cp_async_arrive_noinc(full0 + 8 * s);    // this thread's arrival fires when its copies above have landed
                 ++g;
@@ -415,6 +434,7 @@ __global__ void __launch_bounds__(DENSE ? NTHREADS_DENSE : NTHREADS_SP, 1) gathe
     } else {
         // ================= loader: B tiles + neighbour-table slices, all by bulk copy =================
         const uint32_t tile_bytes = (uint32_t)(2 * B_BYTES);
+        const uint64_t pol_stream = l2_policy_evict_first();       // a table slice is read exactly once
         auto load_table = [&](long long t, int tb) {          // rows of tile t -> nbr_s[tb]
             const long long row0 = (t / ntn) * BM;
             const int rows = (int)min((long long)BM, a.m_out - row0);
@@ -423,10 +443,11 @@ __global__ void __launch_bounds__(DENSE ? NTHREADS_DENSE : NTHREADS_SP, 1) gathe
             if (rows == BM) {                                  // BM * K * 4 bytes: a multiple of 16, 16-byte aligned source
                 if (lane == 0) {
                     mbar_arrive_expect_tx(tblf0 + 8 * tb, (uint32_t)(tbl_ints * 4));
-                    bulk_copy_g2s(smem_u32(dst), src, (uint32_t)(tbl_ints * 4), tblf0 + 8 * tb);
+                    if (a.l2_hints) bulk_copy_g2s_hint(smem_u32(dst), src, (uint32_t)(tbl_ints * 4), tblf0 + 8 * tb, pol_stream);
+                    else bulk_copy_g2s(smem_u32(dst), src, (uint32_t)(tbl_ints * 4), tblf0 + 8 * tb);
                 }
             } else {                                           // ragged last tile: plain copy by the warp
-                for (int e = lane; e < rows * a.K; e += 32) dst[e] = __ldg(src + e);
+                for (int e = lane; e < BM * a.K; e += 32) dst[e] = e < rows * a.K ? __ldg(src + e) : -1;   // producers do not test the row count
                 __threadfence_block();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tblf0 + 8 * tb);
@@ -626,7 +647,8 @@ int32_t gather_gemm_tc(const void *xs, int32_t cin, const float *w, int32_t K, i
     int cin_shift = -1;
     if ((cin & (cin - 1)) == 0)
         for (cin_shift = 0; (1 << cin_shift) < cin; ++cin_shift) {}
-    TcArgs a{bias, scale, shift, residual, reinterpret_cast<const uint8_t *>(xs), wsplit, nbr, tile_counter, tile_masks, out_rows, stats, y, m_out, cin, K, cout, relu, cin_shift};
+    static const int l2_hints = getenv("CPD_L2_HINTS") ? atoi(getenv("CPD_L2_HINTS")) : 1;
+    TcArgs a{bias, scale, shift, residual, reinterpret_cast<const uint8_t *>(xs), wsplit, nbr, tile_counter, tile_masks, out_rows, stats, y, m_out, cin, K, cout, relu, cin_shift, l2_hints};
     static const CUtensorMap no_map{};
     const DenseGeo no_geo{};
     switch (cout) {
@@ -701,7 +723,7 @@ int32_t conv2d_tc(const void *xs, int32_t n, int32_t h, int32_t w_, int32_t cin,
     count_launch();
     int cin_shift = -1;
     TcArgs a{bias, scale, shift, residual, reinterpret_cast<const uint8_t *>(xs), wsplit, nullptr, tile_counter, nullptr, nullptr, stats, y,
-             (long long)n * ho * wo, cin, K, cout, relu, cin_shift};
+             (long long)n * ho * wo, cin, K, cout, relu, cin_shift, 0};
     DenseGeo dg{n, h, w_, ho, wo, kh, kw, pad, (int)div_up(wo, DT_W), (int)div_up(ho, DT_H), out_h, out_w, out_sy, out_sx, out_oy, out_ox};
     switch (bn) {
         case 16: return launch_tc<16, true>(a, xmap, dg, stream);

@@ -138,6 +138,38 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gmem_s
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_size) : "memory");
 }
+// explicit shared-space load (volatile: stays ordered with the barrier waits / copies around it, but carries no "memory"
+// clobber, so several of them can be issued back to back before the first dependent instruction)
+__device__ __forceinline__ int32_t lds_i32(uint32_t smem_addr)
+{
+    int32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_addr));
+    return v;
+}
+// L2 eviction-priority policies (createpolicy): the gathered operand is re-read ~K/2 times per row and should stay, the
+// neighbour table streams through once
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void cp_async16_hint(uint32_t smem_dst, const void *gmem_src, uint32_t src_size, uint64_t policy)
+{
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_size), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s_hint(uint32_t smem_dst, const void *gmem_src, uint32_t bytes, uint32_t bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_dst),
+                 "l"(gmem_src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }

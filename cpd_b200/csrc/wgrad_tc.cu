@@ -27,6 +27,7 @@
 // descriptor's second block aliases whatever follows, which only pollutes accumulator
 // lanes >= AM that are never read.
 #include <algorithm>
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace cpd {
@@ -75,6 +76,7 @@ struct WgArgs {
     float *dw;
     long long m_out;
     int cin, cout, K, rows_per_cta, ci_tiles, taps_per_group;
+    int l2_hints;                // gathers with L2 evict_last (CPD_L2_HINTS, default on)
 };
 
 template <int BN, int AM>
@@ -148,35 +150,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
         for (int j = 0; j < B_V; ++j) b_off[j] = swz_mn(b_row0 + B_RSTEP * j, b_c8);
         const int my_nbr_off = b_t * WINR + b_row0;
         const uint32_t tiles_u32 = smem_u32(tiles);
-        const size_t x_row = (size_t)a.cin * 4, dy_row = (size_t)a.cout * 4;       // image rows: hi(c) | lo(c)
+        const size_t dy_row = (size_t)a.cout * 4;                                  // image rows: hi(c) | lo(c)
+        const uint32_t x_row32 = (uint32_t)a.cin * 4, nbr_w_u32 = smem_u32(nbr_w);
+        const uint64_t pol_keep = l2_policy_evict_last();
         const uint32_t x_lo = (uint32_t)a.cin * 2, dy_lo = (uint32_t)a.cout * 2;
 
         // ---- neighbour-table windows (T x 128 entries): fetched into registers two windows ahead, published into
         //      a double-buffered shared-memory copy one window ahead of the gathers that read it ----
         constexpr int NW = (MAX_T * WINR) / NPROD;      // table entries per thread per window (upper bound)
+        static_assert(NPROD == 2 * WINR, "window mapping: thread -> (tap parity, row), taps advance by 2 per entry");
+        const int wt = tid / WINR, wr = tid % WINR;     // entry q of this thread = (tap wt + 2 q, row wr) of the window
         int32_t nreg[NW];
         auto fetch_window = [&](long long w0) {
+            const long long o = w0 + wr;
+            const bool in = o < r_end;
+            const int32_t *p = a.nbr_t + (long long)(tap0 + wt) * a.m_out + o;
+            const long long step = 2 * a.m_out;
 #pragma unroll
-            for (int q = 0; q < NW; ++q) {
-                const int e = tid + NPROD * q, t = e / WINR, r = e % WINR;
-                const long long o = w0 + r;
-                nreg[q] = (t < T && o < r_end) ? __ldg(a.nbr_t + (long long)(tap0 + t) * a.m_out + o) : -1;
-            }
+            for (int q = 0; q < NW; ++q)
+                nreg[q] = (in && wt + 2 * q < T) ? __ldg(p + q * step) : -1;
         };
         auto publish_window = [&](int buf) {
+            int32_t *dstw = nbr_w + buf * MAX_T * WINR + tid;
 #pragma unroll
-            for (int q = 0; q < NW; ++q) {
-                const int e = tid + NPROD * q;
-                if (e / WINR < T) nbr_w[buf * MAX_T * WINR + e] = nreg[q];
-            }
+            for (int q = 0; q < NW; ++q)
+                if (wt + 2 * q < T) dstw[NPROD * q] = nreg[q];
         };
         auto issue = [&](int blk) {
             const int s = blk % STAGES;
             mbar_wait(empty0 + 8 * s, ((blk / STAGES) & 1) ^ 1);
             const long long r0 = r_begin + (long long)blk * KB;
             const int nvalid = (int)min((long long)KB, r_end - r0);
-            const int32_t *tab = nbr_w + ((blk / (WINR / KB)) & 1) * MAX_T * WINR + my_nbr_off + (blk % (WINR / KB)) * KB;
+            const uint32_t tab = nbr_w_u32 + (uint32_t)((((blk / (WINR / KB)) & 1) * MAX_T * WINR + my_nbr_off + (blk % (WINR / KB)) * KB) * 4);
             const uint32_t dst = tiles_u32 + (uint32_t)(s * STAGE);
+            // neighbour indices FIRST, back to back (each copy below is a compiler barrier: interleaved with the copies the
+            // loads serialise into B_V dependent load -> address -> copy chains per k-block and the warp runs latency-bound)
+            int32_t idx[B_V];
+            if (b_live) {
+#pragma unroll
+                for (int j = 0; j < B_V; ++j) idx[j] = lds_i32(tab + (uint32_t)(B_RSTEP * j * 4));   // rows past r_end carry -1 in the table copy
+            }
 #pragma unroll
             for (int j = 0; j < A_V; ++j) {
                 if (!a_live[j]) continue;
@@ -186,12 +199,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
                 cp_async16(dst + A_BYTES + a_off[j], src + dy_lo, ok ? 16u : 0u);
             }
             if (b_live) {
+                const uint8_t *col_hi = a.xs + (size_t)b_ci * 2, *col_lo = col_hi + x_lo;
 #pragma unroll
                 for (int j = 0; j < B_V; ++j) {
-                    const int32_t idx = tab[B_RSTEP * j];                 // rows past r_end carry -1 in the table copy
-                    const uint8_t *src = a.xs + (size_t)(idx >= 0 ? idx : 0) * x_row + (size_t)b_ci * 2;
-                    cp_async16(dst + 2 * A_BYTES + b_off[j], src, idx >= 0 ? 16u : 0u);
-                    cp_async16(dst + 2 * A_BYTES + B_BYTES + b_off[j], src + x_lo, idx >= 0 ? 16u : 0u);
+                    const uint32_t sz = idx[j] >= 0 ? 16u : 0u;
+                    const uint64_t off = (uint64_t)(uint32_t)max(idx[j], 0) * x_row32;
+                    if (a.l2_hints) {
+                        cp_async16_hint(dst + 2 * A_BYTES + b_off[j], col_hi + off, sz, pol_keep);
+                        cp_async16_hint(dst + 2 * A_BYTES + B_BYTES + b_off[j], col_lo + off, sz, pol_keep);
+                    } else {
+                        cp_async16(dst + 2 * A_BYTES + b_off[j], col_hi + off, sz);
+                        cp_async16(dst + 2 * A_BYTES + B_BYTES + b_off[j], col_lo + off, sz);
+                    }
                 }
             }
         };
@@ -402,7 +421,8 @@ int32_t gather_wgrad_rows_tc(const void *xs, int32_t cin, const void *dys, int64
     long long rows = div_up(div_up(m_out, S), WINR) * WINR;
     S = div_up(m_out, rows);
     CPD_REQUIRE(S <= 65535, CPD_ERR_UNSUPPORTED, "tcgen05 wgrad: too many row slices");
-    WgArgs a{reinterpret_cast<const uint8_t *>(xs), reinterpret_cast<const uint8_t *>(dys), nbr_t, dw, m_out, cin, cout, K, (int)rows, ci_tiles, tpg};
+    static const int l2_hints = getenv("CPD_L2_HINTS") ? atoi(getenv("CPD_L2_HINTS")) : 1;
+    WgArgs a{reinterpret_cast<const uint8_t *>(xs), reinterpret_cast<const uint8_t *>(dys), nbr_t, dw, m_out, cin, cout, K, (int)rows, ci_tiles, tpg, l2_hints};
     dim3 grid(groups, (unsigned)S, ci_tiles * co_tiles);
     if (bn == 256) return launch_wg_am<256>(am, a, grid, stream);
     return launch_wg_am<128>(am, a, grid, stream);
