@@ -255,20 +255,97 @@ class VoxelBackBone8x(_Backbone8xBase):
         return batch_dict
 
 
-class HeightCompression(nn.Module):
-    """map_to_bev/height_compression.py:107-140 (dense + view; bev_align is off in every shipped
-    config).  ``nhwc=True`` writes the BEV map channels-last in one pass and returns it as a
-    (B, C*D, H, W) tensor in torch.channels_last memory format (same logical values)."""
+def _rotate_z(points, angle):
+    """common_utils.rotate_points_along_z for one cloud: points (N, 3), angle scalar tensor."""
+    c, s_ = torch.cos(angle), torch.sin(angle)
+    z, o = torch.zeros_like(c), torch.ones_like(c)
+    rot = torch.stack((c, s_, z, -s_, c, z, z, z, o)).view(3, 3).to(points.dtype)
+    return points @ rot
 
-    def __init__(self, model_cfg=None, nhwc=True, **kwargs):
+
+def x_transform_points(points, param, backward=False):
+    """X_TRAIN.forward_with_param / backward_with_param on points (cpd/datasets/augmentor/X_transform.py:53-160) with the
+    default queue world_rotation -> world_flip (x axis: y := -y) -> world_scaling; param = (angle, flip, scale).
+    backward runs the queue reversed with the inverse rotation / scale (the flip is its own inverse)."""
+    pts = points.clone()
+    if not backward:
+        pts[:, 0:3] = _rotate_z(pts[:, 0:3], param[0])
+        if bool(param[1] != 0):
+            pts[:, 1] = -pts[:, 1]
+        pts[:, 0:3] = pts[:, 0:3] * param[2]
+    else:
+        pts[:, 0:3] = pts[:, 0:3] / param[2]
+        if bool(param[1] != 0):
+            pts[:, 1] = -pts[:, 1]
+        pts[:, 0:3] = _rotate_z(pts[:, 0:3], -param[0])
+    return pts
+
+
+def bilinear_sample_rows(rows, h, w, x, y):
+    """height_compression.py:5-36 (bilinear_interpolate_torch) on an NHWC row matrix: rows (h*w, C) of ONE image, x / y (P,)
+    pixel coordinates -> (P, C).  Corner indices are clamped like the reference's (weights are not)."""
+    x0 = torch.floor(x).long()
+    y0 = torch.floor(y).long()
+    x1, y1 = x0 + 1, y0 + 1
+    x0, x1 = x0.clamp(0, w - 1), x1.clamp(0, w - 1)
+    y0, y1 = y0.clamp(0, h - 1), y1.clamp(0, h - 1)
+    wa = (x1.type_as(x) - x) * (y1.type_as(y) - y)
+    wb = (x1.type_as(x) - x) * (y - y0.type_as(y))
+    wc = (x - x0.type_as(x)) * (y1.type_as(y) - y)
+    wd = (x - x0.type_as(x)) * (y - y0.type_as(y))
+    at = lambda yy, xx: rows.index_select(0, yy * w + xx)
+    return at(y0, x0) * wa[:, None] + at(y1, x0) * wb[:, None] + at(y0, x1) * wc[:, None] + at(y1, x1) * wd[:, None]
+
+
+class HeightCompression(nn.Module):
+    """map_to_bev/height_compression.py:38-175: dense() + view, plus the test-time-augmentation alignment
+    (ALIGN / ALIGN_METHOD in {first, max, mean, weighted_max}, bev_align :81-105).  ``nhwc=True`` writes the BEV map
+    channels-last in one pass and returns it as a (B, C*D, H, W) tensor in torch.channels_last memory format (same
+    logical values), which is also the layout bev_align samples from (a pixel is one contiguous row)."""
+
+    def __init__(self, model_cfg=None, nhwc=True, num_frames=1, voxel_size=None, point_cloud_range=None, **kwargs):
         super().__init__()
         self.model_cfg = _cfg(model_cfg)
         self.num_bev_features = self.model_cfg.get("NUM_BEV_FEATURES", 256)
         self.nhwc = nhwc
+        self.num_frames = num_frames
+        self.voxel_size, self.point_cloud_range = voxel_size, point_cloud_range
+        self._grids = {}
+
+    def get_pseudo_points(self, pts_range, voxel_size, stride, device):
+        """:48-66: centres of the stride-downsampled BEV pixels as (H, W, 3) points, z = 0 (float64 arange like numpy's)."""
+        key = (tuple(float(v) for v in pts_range), tuple(float(v) for v in voxel_size), int(stride), str(device))
+        if key not in self._grids:
+            import numpy as np
+            xs, ys = voxel_size[0] * stride, voxel_size[1] * stride
+            x = np.arange(pts_range[0] + xs / 2, pts_range[3], xs)
+            y = np.arange(pts_range[1] + ys / 2, pts_range[4] + ys / 2, ys)
+            x, y = np.meshgrid(x, y)
+            g = np.stack([x, y, np.zeros_like(x)]).astype(np.float32)
+            self._grids[key] = torch.from_numpy(g).permute(1, 2, 0).contiguous().to(device)
+        return self._grids[key]
+
+    def bev_align(self, bev_feat, transform_param, stride, stage_i):
+        """:81-105: resample stage i's BEV map onto stage 0's frame.  bev_feat (B, C, H, W) (any memory format);
+        transform_param (B, stages, 3)."""
+        n, c, h, w = bev_feat.shape
+        rows = bev_feat.permute(0, 2, 3, 1).reshape(n, h * w, c)              # a view for channels_last maps
+        pr, vs = self.point_cloud_range, self.voxel_size
+        out = []
+        for b in range(n):
+            grid = self.get_pseudo_points(pr, vs, stride, bev_feat.device).reshape(-1, 3)
+            pts = x_transform_points(grid, transform_param[b][stage_i])
+            pts = x_transform_points(pts, transform_param[b][0], backward=True)
+            x = (pts[:, 0] - pr[0]) / vs[0] / stride
+            y = (pts[:, 1] - pr[1]) / vs[1] / stride
+            out.append(bilinear_sample_rows(rows[b], h, w, x, y).reshape(h, w, c))
+        return torch.stack(out).permute(0, 3, 1, 2)                           # logical NCHW over NHWC memory
 
     def forward(self, batch_dict):
         stages = batch_dict["transform_param"].shape[1] if "transform_param" in batch_dict else 1
         batch_dict["spatial_features_stride"] = batch_dict["encoded_spconv_tensor_stride"]
+        align = "transform_param" in batch_dict and self.model_cfg.get("ALIGN", False)
+        all_feat = []
         for i in range(stages):
             sid = "" if i == 0 else str(i)
             t = batch_dict["encoded_spconv_tensor" + sid]
@@ -279,4 +356,18 @@ class HeightCompression(nn.Module):
                 n, c, dd, h, w = d.shape
                 sf = d.view(n, c * dd, h, w)
             batch_dict["spatial_features" + sid] = sf
+            if i == 0:
+                all_feat.append(sf)
+            elif align:
+                all_feat.append(self.bev_align(sf, batch_dict["transform_param"], batch_dict["spatial_features_stride"], i))
+        if align:
+            method = self.model_cfg.get("ALIGN_METHOD", "first")
+            stack = torch.stack(all_feat)
+            if method == "max":
+                batch_dict["spatial_features"] = stack.max(0)[0]
+            elif method == "mean":
+                batch_dict["spatial_features"] = stack.mean(0)
+            elif method == "weighted_max":
+                w1, w2 = self.model_cfg.get("W1", 0.9), self.model_cfg.get("W2", 0.1)
+                batch_dict["spatial_features"] = w1 * batch_dict["spatial_features"] + w2 * stack.max(0)[0]
         return batch_dict

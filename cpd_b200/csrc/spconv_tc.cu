@@ -100,7 +100,8 @@ struct TcArgs {
     long long m_out;
     int cin, K, cout, relu;
     int cin_shift;              // log2(cin) when cin is a power of two (every CPD layer), else -1
-    int l2_hints;               // gathers with L2 evict_last, table slices with evict_first (CPD_L2_HINTS, default on)
+    int l2_hints;               // gathers with L2 evict_last, table slices with evict_first (CPD_L2_HINTS; measured neutral, default off)
+    int debug;                  // CPD_TC_DEBUG (timing experiments only, results are WRONG): 1 = no zero-fill copies, 2 = no MMAs, 4 = no epilogue stores
 };
 
 // DENSE variant (cpd_conv2d_fwd / cpd_conv2d_dgrad: the dense BEV convolutions, stride 1): the rows of an output tile are a
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(DENSE ? NTHREADS_DENSE : NTHREADS_SP, 1) gathe
                     for (int j = 0; j < 16; ++j) { x[j] = valid ? o[j] : 0.f; x[16 + j] = x[j] * x[j]; }
                     st_acc[i] += warp_transpose_reduce(x, lane);
                 }
-                if (valid) {
+                if (valid && !((a.debug & 4) && o[0] != 12345.678f)) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         float4 r = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(DENSE ? NTHREADS_DENSE : NTHREADS_SP, 1) gathe
                 } else {
 #pragma unroll
                     for (int j = 0; j < A_V; ++j) {
-                        const uint32_t sz = idx[j] >= 0 ? 16u : 0u;
+                        const uint32_t sz = (idx[j] >= 0 || (a.debug & 1)) ? 16u : 0u;
                         const uint64_t off = (uint64_t)(uint32_t)max(idx[j], 0) * row_bytes;
                         cp_async16(dst + soff[j], col_hi + off, sz);
                         cp_async16(dst + A_BYTES + soff[j], col_lo + off, sz);
@@ -398,12 +399,13 @@ __global__ void __launch_bounds__(DENSE ? NTHREADS_DENSE : NTHREADS_SP, 1) gathe
                 fence_async_smem();        // the producers' cp.async writes (generic proxy), observed through the barrier -> async proxy
                 tc_fence_after();
                 if (elect_one()) {
+                    const bool no_mma = (a.debug & 2) && !(first);          // (timing experiment: only the tile's first k-block runs)
                     const uint64_t a_hi = DESC_HI | (uint64_t)(((tiles_u32 + (uint32_t)(s * STAGE)) & 0x3FFFFu) >> 4);
                     const uint64_t a_lo = a_hi + (A_BYTES >> 4), b_hi = a_hi + (2 * A_BYTES >> 4), b_lo = b_hi + (B_BYTES >> 4);
                     const int k16n = kb == n_kb - 1 ? last_k16 : BKE / 16;
 #pragma unroll
                     for (int k16 = 0; k16 < BKE / 16; ++k16) {
-                        if (k16 < k16n) {
+                        if (k16 < k16n && !no_mma) {
                             const uint64_t adv = (uint64_t)(k16 * 2);            // +32 bytes along K inside the swizzle row
                             if (BN <= 128) {
                                 if (first && k16 == 0) umma_bf16_set(d_main, a_hi, b_hi, IDESC2);
@@ -647,8 +649,9 @@ int32_t gather_gemm_tc(const void *xs, int32_t cin, const float *w, int32_t K, i
     int cin_shift = -1;
     if ((cin & (cin - 1)) == 0)
         for (cin_shift = 0; (1 << cin_shift) < cin; ++cin_shift) {}
-    static const int l2_hints = getenv("CPD_L2_HINTS") ? atoi(getenv("CPD_L2_HINTS")) : 1;
-    TcArgs a{bias, scale, shift, residual, reinterpret_cast<const uint8_t *>(xs), wsplit, nbr, tile_counter, tile_masks, out_rows, stats, y, m_out, cin, K, cout, relu, cin_shift, l2_hints};
+    static const int l2_hints = getenv("CPD_L2_HINTS") ? atoi(getenv("CPD_L2_HINTS")) : 0;
+    static const int debug = getenv("CPD_TC_DEBUG") ? atoi(getenv("CPD_TC_DEBUG")) : 0;
+    TcArgs a{bias, scale, shift, residual, reinterpret_cast<const uint8_t *>(xs), wsplit, nbr, tile_counter, tile_masks, out_rows, stats, y, m_out, cin, K, cout, relu, cin_shift, l2_hints, debug};
     static const CUtensorMap no_map{};
     const DenseGeo no_geo{};
     switch (cout) {
@@ -723,7 +726,7 @@ int32_t conv2d_tc(const void *xs, int32_t n, int32_t h, int32_t w_, int32_t cin,
     count_launch();
     int cin_shift = -1;
     TcArgs a{bias, scale, shift, residual, reinterpret_cast<const uint8_t *>(xs), wsplit, nullptr, tile_counter, nullptr, nullptr, stats, y,
-             (long long)n * ho * wo, cin, K, cout, relu, cin_shift, 0};
+             (long long)n * ho * wo, cin, K, cout, relu, cin_shift, 0, 0};
     DenseGeo dg{n, h, w_, ho, wo, kh, kw, pad, (int)div_up(wo, DT_W), (int)div_up(ho, DT_H), out_h, out_w, out_sy, out_sx, out_oy, out_ox};
     switch (bn) {
         case 16: return launch_tc<16, true>(a, xmap, dg, stream);

@@ -36,6 +36,8 @@ using namespace tc;
 
 constexpr int KB = 32;           // rows per k-block (2 MMA K-steps of 16)
 constexpr int WINR = 128;        // rows per neighbour-table window (4 k-blocks)
+constexpr int WSTR = WINR + 1;   // pitch of a tap's row in the shared-memory window: the lanes of a warp read the SAME row of up to
+                                 // 16 different taps, a pitch of 128 words put all of them in one bank (ncu: 17.6 M conflicts per launch)
 constexpr int NPW = 8;            // producer / epilogue warps
 constexpr int NPROD = NPW * 32;
 constexpr int NTHREADS = NPROD + 32;
@@ -95,8 +97,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    int32_t *nbr_w = reinterpret_cast<int32_t *>(tiles + STAGES * STAGE);       // [2][MAX_T][WINR]  (also the over-read slack)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(nbr_w + 2 * MAX_T * WINR);    // full[S], empty[S], accum
+    int32_t *nbr_w = reinterpret_cast<int32_t *>(tiles + STAGES * STAGE);       // [2][MAX_T][WSTR]  (also the over-read slack)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(nbr_w + 2 * MAX_T * WSTR + 2);  // (+2: keeps the barriers 8-byte aligned)    // full[S], empty[S], accum
     uint32_t *info = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);       // [S] k8 steps valid in the stage / END
     uint32_t *misc = info + STAGES;                                             // [0] tmem base
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum_bar = smem_u32(bars + 2 * STAGES);
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
         uint32_t b_off[B_V];
 #pragma unroll
         for (int j = 0; j < B_V; ++j) b_off[j] = swz_mn(b_row0 + B_RSTEP * j, b_c8);
-        const int my_nbr_off = b_t * WINR + b_row0;
+        const int my_nbr_off = b_t * WSTR + b_row0;
         const uint32_t tiles_u32 = smem_u32(tiles);
         const size_t dy_row = (size_t)a.cout * 4;                                  // image rows: hi(c) | lo(c)
         const uint32_t x_row32 = (uint32_t)a.cin * 4, nbr_w_u32 = smem_u32(nbr_w);
@@ -171,17 +173,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
                 nreg[q] = (in && wt + 2 * q < T) ? __ldg(p + q * step) : -1;
         };
         auto publish_window = [&](int buf) {
-            int32_t *dstw = nbr_w + buf * MAX_T * WINR + tid;
+            int32_t *dstw = nbr_w + buf * MAX_T * WSTR + wt * WSTR + wr;
 #pragma unroll
             for (int q = 0; q < NW; ++q)
-                if (wt + 2 * q < T) dstw[NPROD * q] = nreg[q];
+                if (wt + 2 * q < T) dstw[2 * WSTR * q] = nreg[q];
         };
         auto issue = [&](int blk) {
             const int s = blk % STAGES;
             mbar_wait(empty0 + 8 * s, ((blk / STAGES) & 1) ^ 1);
             const long long r0 = r_begin + (long long)blk * KB;
             const int nvalid = (int)min((long long)KB, r_end - r0);
-            const uint32_t tab = nbr_w_u32 + (uint32_t)((((blk / (WINR / KB)) & 1) * MAX_T * WINR + my_nbr_off + (blk % (WINR / KB)) * KB) * 4);
+            const uint32_t tab = nbr_w_u32 + (uint32_t)((((blk / (WINR / KB)) & 1) * MAX_T * WSTR + my_nbr_off + (blk % (WINR / KB)) * KB) * 4);
             const uint32_t dst = tiles_u32 + (uint32_t)(s * STAGE);
             // neighbour indices FIRST, back to back (each copy below is a compiler barrier: interleaved with the copies the
             // loads serialise into B_V dependent load -> address -> copy chains per k-block and the warp runs latency-bound)
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
 template <int BN, int AM>
 constexpr size_t wg_smem()
 {
-    return 1024 + (size_t)w_stages(BN, AM) * w_stage_bytes(BN, AM) + 2 * MAX_T * WINR * 4 + (2 * w_stages(BN, AM) + 1) * 8 +
+    return 1024 + (size_t)w_stages(BN, AM) * w_stage_bytes(BN, AM) + (2 * MAX_T * WSTR + 2) * 4 + (2 * w_stages(BN, AM) + 1) * 8 +
            (w_stages(BN, AM) + 8) * 4;
 }
 
@@ -421,7 +423,7 @@ int32_t gather_wgrad_rows_tc(const void *xs, int32_t cin, const void *dys, int64
     long long rows = div_up(div_up(m_out, S), WINR) * WINR;
     S = div_up(m_out, rows);
     CPD_REQUIRE(S <= 65535, CPD_ERR_UNSUPPORTED, "tcgen05 wgrad: too many row slices");
-    static const int l2_hints = getenv("CPD_L2_HINTS") ? atoi(getenv("CPD_L2_HINTS")) : 1;
+    static const int l2_hints = getenv("CPD_L2_HINTS") ? atoi(getenv("CPD_L2_HINTS")) : 0;
     WgArgs a{reinterpret_cast<const uint8_t *>(xs), reinterpret_cast<const uint8_t *>(dys), nbr_t, dw, m_out, cin, cout, K, (int)rows, ci_tiles, tpg, l2_hints};
     dim3 grid(groups, (unsigned)S, ci_tiles * co_tiles);
     if (bn == 256) return launch_wg_am<256>(am, a, grid, stream);

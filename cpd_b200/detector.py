@@ -11,7 +11,7 @@ host memory); nothing on this path runs on the CPU.
 import torch
 import torch.nn as nn
 
-from . import backbone, bev, voxel
+from . import backbone, bev, roipool, voxel
 from .synth import PC_RANGE, VOXEL_SIZE
 
 MODEL_CFG = dict(
@@ -57,8 +57,12 @@ class CPDHotPathDetector(nn.Module):
 
     def __init__(self, model_cfg=None, pc_range=PC_RANGE, voxel_size=VOXEL_SIZE, num_point_features=5, max_pts=5,
                  max_voxels=1000000, class_names=("Vehicle", "Pedestrian", "Cyclist"), res_backbone=True,
-                 predict_boxes_when_training=True, device_point_pipeline=False):
+                 predict_boxes_when_training=True, device_point_pipeline=False, roi_grid_pool=False, rois_per_image=128):
         super().__init__()
+        # roi_grid_pool: the pooling stage of VoxelRCNNProtoHead consumes x_conv3 / x_conv4 of BOTH towers on the
+        # CenterHead's proposals, as voxel_rcnn_head.py:186-343 does; its FC / loss layers stay out of scope, so the pooled
+        # features end in a stand-in loss.  Off by default: BASELINE configs[2] = backbone + BEV head + iou3d_nms.
+        self.rois_per_image = rois_per_image
         # device_point_pipeline: run the dataset-side point pipeline (range mask + train-time shuffle,
         # data_processor.py:77-126) on the device, after the H2D copy of the RAW sweep
         self.device_point_pipeline = device_point_pipeline
@@ -81,6 +85,13 @@ class CPDHotPathDetector(nn.Module):
         self.dense_head = bev.CenterHead(cfg["DENSE_HEAD"], 1, self.backbone_2d.num_bev_features_post, len(class_names),
                                          class_names, grid, self.pc_range, self.voxel_size,
                                          predict_boxes_when_training=predict_boxes_when_training)
+        self.roi_pool = self.roi_pool_mm = None
+        if roi_grid_pool:
+            assert predict_boxes_when_training, "RoI grid pooling needs the CenterHead's proposals"
+            nf = self.backbone_3d.num_point_features
+            chans = nf if isinstance(nf, dict) else {"x_conv3": 64, "x_conv4": 128}
+            self.roi_pool = roipool.RoIGridPool(chans, self.voxel_size, self.pc_range)            # roi_grid_pool_layers
+            self.roi_pool_mm = roipool.RoIGridPool(chans, self.voxel_size, self.pc_range)         # roi_grid_pool_layers_mm
 
     def _voxelize(self, frames, device):
         frames = [f if f.is_cuda else f.to(device, non_blocking=True) for f in frames]
@@ -182,9 +193,18 @@ class CPDHotPathDetector(nn.Module):
         self.last_batch_dict = bd
         if self.training:
             loss, tb = self.dense_head.get_loss()
-            if "multi_scale_3d_features_mm" in bd:
-                # the reference feeds the MM tower to the RoI head (out of scope); a tiny
-                # regulariser stands in for that consumer so its parameters receive gradients
+            if self.roi_pool is not None:
+                # RoI grid pooling on both towers (voxel_rcnn_head.py:186-343): the real consumer of x_conv3 / x_conv4
+                rois = bd["rois"][:, :self.rois_per_image, :7].detach()
+                strides = bd["multi_scale_3d_strides"]
+                pooled = self.roi_pool(rois, bd["multi_scale_3d_features"], strides)
+                tb["roi_pooled_abs_mean"] = pooled.detach().abs().mean()
+                loss = loss + 1e-2 * pooled.square().mean()
+                if "multi_scale_3d_features_mm" in bd:
+                    loss = loss + 1e-2 * self.roi_pool_mm(rois, bd["multi_scale_3d_features_mm"], strides).square().mean()
+            elif "multi_scale_3d_features_mm" in bd:
+                # without the pooling stage a tiny regulariser stands in for the MM tower's consumer so its parameters
+                # receive gradients
                 loss = loss + 1e-3 * sum(t.features.square().mean() for t in bd["multi_scale_3d_features_mm"].values())
             return loss, tb
         return bd["final_box_dicts"]

@@ -169,3 +169,26 @@ def _sa_module_and_pool(cuda, roipool):
     pooled.square().mean().backward()
     assert t3.features.grad is not None and t4.features.grad is not None and float(t3.features.grad.abs().sum()) > 0
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in pool.parameters())
+
+
+def test_detector_train_step_with_roi_grid_pool(cuda):
+    """CPDHotPathDetector(roi_grid_pool=True): the CenterHead's proposals are pooled from x_conv3 / x_conv4 of both towers
+    (voxel_rcnn_head.py:186-343) instead of the stand-in regulariser; every pooling and tower parameter receives a gradient."""
+    import numpy as np
+
+    from cpd_b200 import detector
+    from cpd_b200.synth import synth_gt_boxes
+    torch.manual_seed(0)
+    det = detector.CPDHotPathDetector(roi_grid_pool=True, rois_per_image=16).to(cuda).train()
+    bs = 2
+    batch = dict(points=[torch.from_numpy(synth_scan(20000, 90 + i)).to(cuda) for i in range(bs)],
+                 points1=[torch.from_numpy(synth_scan(20000, 590 + i)).to(cuda) for i in range(bs)],
+                 gt_boxes=torch.from_numpy(np.stack([synth_gt_boxes(30, 90 + i) for i in range(bs)])).to(cuda))
+    loss, tb = det(batch)
+    assert torch.isfinite(loss) and "roi_pooled_abs_mean" in tb
+    loss.backward()
+    for name, p in det.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+    for pool in (det.roi_pool, det.roi_pool_mm):
+        assert any(float(p.grad.abs().sum()) > 0 for p in pool.parameters())
+    assert float(det.backbone_3d.conv4_2[1].conv2.weight.grad.abs().sum()) > 0      # the MM tower trains through the pooling stage
