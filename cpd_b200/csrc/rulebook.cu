@@ -43,42 +43,60 @@ __global__ void hash_insert_kernel(const int32_t *__restrict__ coords, long long
 
 struct Ker { int kd, kh, kw, sd, sh, sw, pd, ph, pw; };
 
-// thread per (row, tap)
-__global__ void subm_table_kernel(const int32_t *__restrict__ coords, long long m, Geo g, Ker k, HashView h,
+// The table kernels run one thread per (row, tap).  Their arithmetic is index decoding -- t / K, tap % kw, n % stride -- which
+// with RUNTIME divisors costs more than the hash probe it guards (64-bit division by K alone is ~40 instructions).  The
+// geometries of the CPD towers are fixed (3x3x3 stride 1 / stride 2, 3x1x1 stride 2x1x1), so the kernels are instantiated
+// with those constants (template value 0 = read the runtime field) and a 32-bit flat index whenever m * K fits.
+template <int KD, int KH, int KW, int SD, int SH, int SW>
+struct KerC {
+    const Ker &k;
+    __device__ __forceinline__ int kd() const { return KD ? KD : k.kd; }
+    __device__ __forceinline__ int kh() const { return KH ? KH : k.kh; }
+    __device__ __forceinline__ int kw() const { return KW ? KW : k.kw; }
+    __device__ __forceinline__ int sd() const { return SD ? SD : k.sd; }
+    __device__ __forceinline__ int sh() const { return SH ? SH : k.sh; }
+    __device__ __forceinline__ int sw() const { return SW ? SW : k.sw; }
+};
+
+template <typename IdxT, int KD, int KH, int KW>
+__global__ void subm_table_kernel(const int32_t *__restrict__ coords, long long m, Geo g, Ker k_, HashView h,
                                   int32_t *__restrict__ nbr)
 {
-    const int K = k.kd * k.kh * k.kw;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m * K) return;
-    long long o = t / K;
-    int tap = (int)(t - o * K);
-    int kx = tap % k.kw, ky = (tap / k.kw) % k.kh, kz = tap / (k.kw * k.kh);
-    int4 c = __ldg(reinterpret_cast<const int4 *>(coords) + o);
-    int z = c.y + kz - k.kd / 2, y = c.z + ky - k.kh / 2, x = c.w + kx - k.kw / 2;
+    const KerC<KD, KH, KW, 1, 1, 1> k{k_};
+    const int K = k.kd() * k.kh() * k.kw();
+    const IdxT t = (IdxT)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((long long)t >= m * K) return;
+    const IdxT o = t / (IdxT)K;
+    const int tap = (int)(t - o * (IdxT)K);
+    const int kx = tap % k.kw(), ky = (tap / k.kw()) % k.kh(), kz = tap / (k.kw() * k.kh());
+    const int4 c = __ldg(reinterpret_cast<const int4 *>(coords) + o);
+    const int z = c.y + kz - k.kd() / 2, y = c.z + ky - k.kh() / 2, x = c.w + kx - k.kw() / 2;
     int32_t r = -1;
     if (z >= 0 && y >= 0 && x >= 0 && z < g.d && y < g.h && x < g.w)
-        r = (kz == k.kd / 2 && ky == k.kh / 2 && kx == k.kw / 2) ? (int32_t)o : hash_find(h, lin_key(g, c.x, z, y, x));
+        r = (kz == k.kd() / 2 && ky == k.kh() / 2 && kx == k.kw() / 2) ? (int32_t)o : hash_find(h, lin_key(g, c.x, z, y, x));
     nbr[t] = r;
 }
 
 // strided conv, step 1: every (input, tap) marks its output cell in the bitmap
-__global__ void strided_mark_kernel(const int32_t *__restrict__ coords, long long m, Geo go, Ker k,
+template <typename IdxT, int KD, int KH, int KW, int SD, int SH, int SW>
+__global__ void strided_mark_kernel(const int32_t *__restrict__ coords, long long m, Geo go, Ker k_,
                                     uint32_t *__restrict__ bitmap)
 {
-    const int K = k.kd * k.kh * k.kw;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m * K) return;
-    long long i = t / K;
-    int tap = (int)(t - i * K);
-    int kx = tap % k.kw, ky = (tap / k.kw) % k.kh, kz = tap / (k.kw * k.kh);
-    int4 c = __ldg(reinterpret_cast<const int4 *>(coords) + i);
-    int nz = c.y + k.pd - kz, ny = c.z + k.ph - ky, nx = c.w + k.pw - kx;
+    const KerC<KD, KH, KW, SD, SH, SW> k{k_};
+    const int K = k.kd() * k.kh() * k.kw();
+    const IdxT t = (IdxT)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((long long)t >= m * K) return;
+    const IdxT i = t / (IdxT)K;
+    const int tap = (int)(t - i * (IdxT)K);
+    const int kx = tap % k.kw(), ky = (tap / k.kw()) % k.kh(), kz = tap / (k.kw() * k.kh());
+    const int4 c = __ldg(reinterpret_cast<const int4 *>(coords) + i);
+    const int nz = c.y + k_.pd - kz, ny = c.z + k_.ph - ky, nx = c.w + k_.pw - kx;
     if (nz < 0 || ny < 0 || nx < 0) return;
-    if (nz % k.sd || ny % k.sh || nx % k.sw) return;
-    int z = nz / k.sd, y = ny / k.sh, x = nx / k.sw;
+    if (nz % k.sd() || ny % k.sh() || nx % k.sw()) return;
+    const int z = nz / k.sd(), y = ny / k.sh(), x = nx / k.sw();
     if (z >= go.d || y >= go.h || x >= go.w) return;
-    uint32_t key = lin_key(go, c.x, z, y, x);
-    uint32_t bit = 1u << (key & 31);
+    const uint32_t key = lin_key(go, c.x, z, y, x);
+    const uint32_t bit = 1u << (key & 31);
     uint32_t *wd = bitmap + (key >> 5);
     if (!(*wd & bit)) atomicOr(wd, bit);   // plain read first: most cells are marked 4-8 times
 }
@@ -152,41 +170,77 @@ __global__ void __launch_bounds__(SCAN_THREADS) bitmap_compact(const uint32_t *_
 }
 
 // nbr_fwd: thread per (output row, tap): input at o*s - p + k
-__global__ void strided_fwd_table_kernel(const int32_t *__restrict__ out_coords, long long m_out, Geo gi, Ker k,
+template <typename IdxT, int KD, int KH, int KW, int SD, int SH, int SW>
+__global__ void strided_fwd_table_kernel(const int32_t *__restrict__ out_coords, long long m_out, Geo gi, Ker k_,
                                          HashView hin, int32_t *__restrict__ nbr)
 {
-    const int K = k.kd * k.kh * k.kw;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m_out * K) return;
-    long long o = t / K;
-    int tap = (int)(t - o * K);
-    int kx = tap % k.kw, ky = (tap / k.kw) % k.kh, kz = tap / (k.kw * k.kh);
-    int4 c = __ldg(reinterpret_cast<const int4 *>(out_coords) + o);
-    int z = c.y * k.sd - k.pd + kz, y = c.z * k.sh - k.ph + ky, x = c.w * k.sw - k.pw + kx;
+    const KerC<KD, KH, KW, SD, SH, SW> k{k_};
+    const int K = k.kd() * k.kh() * k.kw();
+    const IdxT t = (IdxT)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((long long)t >= m_out * K) return;
+    const IdxT o = t / (IdxT)K;
+    const int tap = (int)(t - o * (IdxT)K);
+    const int kx = tap % k.kw(), ky = (tap / k.kw()) % k.kh(), kz = tap / (k.kw() * k.kh());
+    const int4 c = __ldg(reinterpret_cast<const int4 *>(out_coords) + o);
+    const int z = c.y * k.sd() - k_.pd + kz, y = c.z * k.sh() - k_.ph + ky, x = c.w * k.sw() - k_.pw + kx;
     int32_t r = -1;
     if (z >= 0 && y >= 0 && x >= 0 && z < gi.d && y < gi.h && x < gi.w) r = hash_find(hin, lin_key(gi, c.x, z, y, x));
     nbr[t] = r;
 }
 
 // nbr_bwd: thread per (input row, tap): output at (i + p - k)/s when divisible
-__global__ void strided_bwd_table_kernel(const int32_t *__restrict__ in_coords, long long m_in, Geo go, Ker k,
+template <typename IdxT, int KD, int KH, int KW, int SD, int SH, int SW>
+__global__ void strided_bwd_table_kernel(const int32_t *__restrict__ in_coords, long long m_in, Geo go, Ker k_,
                                          HashView hout, int32_t *__restrict__ nbr)
 {
-    const int K = k.kd * k.kh * k.kw;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m_in * K) return;
-    long long i = t / K;
-    int tap = (int)(t - i * K);
-    int kx = tap % k.kw, ky = (tap / k.kw) % k.kh, kz = tap / (k.kw * k.kh);
-    int4 c = __ldg(reinterpret_cast<const int4 *>(in_coords) + i);
-    int nz = c.y + k.pd - kz, ny = c.z + k.ph - ky, nx = c.w + k.pw - kx;
+    const KerC<KD, KH, KW, SD, SH, SW> k{k_};
+    const int K = k.kd() * k.kh() * k.kw();
+    const IdxT t = (IdxT)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((long long)t >= m_in * K) return;
+    const IdxT i = t / (IdxT)K;
+    const int tap = (int)(t - i * (IdxT)K);
+    const int kx = tap % k.kw(), ky = (tap / k.kw()) % k.kh(), kz = tap / (k.kw() * k.kh());
+    const int4 c = __ldg(reinterpret_cast<const int4 *>(in_coords) + i);
+    const int nz = c.y + k_.pd - kz, ny = c.z + k_.ph - ky, nx = c.w + k_.pw - kx;
     int32_t r = -1;
-    if (nz >= 0 && ny >= 0 && nx >= 0 && !(nz % k.sd) && !(ny % k.sh) && !(nx % k.sw)) {
-        int z = nz / k.sd, y = ny / k.sh, x = nx / k.sw;
+    if (nz >= 0 && ny >= 0 && nx >= 0 && !(nz % k.sd()) && !(ny % k.sh()) && !(nx % k.sw())) {
+        const int z = nz / k.sd(), y = ny / k.sh(), x = nx / k.sw();
         if (z < go.d && y < go.h && x < go.w) r = hash_find(hout, lin_key(go, c.x, z, y, x));
     }
     nbr[t] = r;
 }
+
+// Instantiation choice: the three geometries of the CPD towers get constants, everything else the runtime kernel.
+enum GeoClass { GEO_RUNTIME = 0, GEO_333_S1, GEO_333_S2, GEO_311_S211 };
+inline GeoClass geo_class(const Ker &k)
+{
+    if (k.kd == 3 && k.kh == 3 && k.kw == 3 && k.sd == 1 && k.sh == 1 && k.sw == 1) return GEO_333_S1;
+    if (k.kd == 3 && k.kh == 3 && k.kw == 3 && k.sd == 2 && k.sh == 2 && k.sw == 2) return GEO_333_S2;
+    if (k.kd == 3 && k.kh == 1 && k.kw == 1 && k.sd == 2 && k.sh == 1 && k.sw == 1) return GEO_311_S211;
+    return GEO_RUNTIME;
+}
+// KERNEL<IdxT, constants...><<<grid, 256, 0, stream>>>(args...) for the geometry class of k and the index width of n threads
+#define CPD_GEO_LAUNCH(KERNEL, k, n, stream, ...)                                                                              \
+    do {                                                                                                                      \
+        const unsigned grid_ = (unsigned)div_up((long long)(n), 256);                                                         \
+        const bool small_ = (long long)(n) + 256 < 0xFFFFFFFFll;                                                              \
+        switch (geo_class(k)) {                                                                                               \
+            case GEO_333_S1:                                                                                                  \
+                if (small_) KERNEL<uint32_t, 3, 3, 3, 1, 1, 1><<<grid_, 256, 0, stream>>>(__VA_ARGS__);                       \
+                else KERNEL<long long, 3, 3, 3, 1, 1, 1><<<grid_, 256, 0, stream>>>(__VA_ARGS__);                             \
+                break;                                                                                                        \
+            case GEO_333_S2:                                                                                                  \
+                if (small_) KERNEL<uint32_t, 3, 3, 3, 2, 2, 2><<<grid_, 256, 0, stream>>>(__VA_ARGS__);                       \
+                else KERNEL<long long, 3, 3, 3, 2, 2, 2><<<grid_, 256, 0, stream>>>(__VA_ARGS__);                             \
+                break;                                                                                                        \
+            case GEO_311_S211:                                                                                                \
+                if (small_) KERNEL<uint32_t, 3, 1, 1, 2, 1, 1><<<grid_, 256, 0, stream>>>(__VA_ARGS__);                       \
+                else KERNEL<long long, 3, 1, 1, 2, 1, 1><<<grid_, 256, 0, stream>>>(__VA_ARGS__);                             \
+                break;                                                                                                        \
+            default:                                                                                                          \
+                KERNEL<long long, 0, 0, 0, 0, 0, 0><<<grid_, 256, 0, stream>>>(__VA_ARGS__);                                  \
+        }                                                                                                                     \
+    } while (0)
 
 int32_t make_geo(const int32_t *shape3, int32_t batch, Geo *g, const char *who)
 {
@@ -260,7 +314,10 @@ extern "C" int32_t cpd_rulebook_subm(const int32_t *coords, int64_t m, const int
     CPD_REQUIRE(m >= 0 && nbr && ((uintptr_t)coords & 15) == 0, CPD_ERR_BAD_ARG, "cpd_rulebook_subm: bad m/nbr/coords alignment");
     long long t = m * (long long)(k.kd * k.kh * k.kw);
     if (t > 0) {
-        subm_table_kernel<<<(unsigned)div_up(t, 256), 256, 0, stream>>>(coords, m, g, k, h, nbr);
+        if (k.kd == 3 && k.kh == 3 && k.kw == 3 && t + 256 < 0xFFFFFFFFll)
+            subm_table_kernel<uint32_t, 3, 3, 3><<<(unsigned)div_up(t, 256), 256, 0, stream>>>(coords, m, g, k, h, nbr);
+        else
+            subm_table_kernel<long long, 0, 0, 0><<<(unsigned)div_up(t, 256), 256, 0, stream>>>(coords, m, g, k, h, nbr);
         count_launch();
     }
     return launch_status("cpd_rulebook_subm");
@@ -310,7 +367,7 @@ extern "C" int32_t cpd_rulebook_strided_outputs(const int32_t *coords, int64_t m
     int32_t *block_sums = (int32_t *)((char *)ws + align_up((size_t)nwords * 4 + 16, 256));
     CPD_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)nwords * 4 + 16, stream));
     long long t = m * (long long)(k.kd * k.kh * k.kw);
-    if (t > 0) strided_mark_kernel<<<(unsigned)div_up(t, 256), 256, 0, stream>>>(coords, m, go, k, bitmap);
+    if (t > 0) CPD_GEO_LAUNCH(strided_mark_kernel, k, t, stream, coords, m, go, k, bitmap);
     bitmap_block_count<<<nblk, SCAN_THREADS, 0, stream>>>(bitmap, nwords, block_sums);
     scan_block_sums<<<1, SCAN_THREADS, 0, stream>>>(block_sums, nblk, n_out);
     bitmap_compact<<<nblk, SCAN_THREADS, 0, stream>>>(bitmap, nwords, block_sums, go, cap_out, out_coords);
@@ -336,14 +393,14 @@ extern "C" int32_t cpd_rulebook_strided_tables(const int32_t *in_coords, int64_t
     if (nbr_fwd) {
         if ((st = view_hash(in_hash, in_hash_bytes, &hin, "cpd_rulebook_strided_tables"))) return st;
         if (m_out > 0) {
-            strided_fwd_table_kernel<<<(unsigned)div_up(m_out * K, 256), 256, 0, stream>>>(out_coords, m_out, gi, k, hin, nbr_fwd);
+            CPD_GEO_LAUNCH(strided_fwd_table_kernel, k, m_out * K, stream, out_coords, m_out, gi, k, hin, nbr_fwd);
             count_launch();
         }
     }
     if (nbr_bwd) {
         if ((st = view_hash(out_hash, out_hash_bytes, &hout, "cpd_rulebook_strided_tables"))) return st;
         if (m_in > 0) {
-            strided_bwd_table_kernel<<<(unsigned)div_up(m_in * K, 256), 256, 0, stream>>>(in_coords, m_in, go, k, hout, nbr_bwd);
+            CPD_GEO_LAUNCH(strided_bwd_table_kernel, k, m_in * K, stream, in_coords, m_in, go, k, hout, nbr_bwd);
             count_launch();
         }
     }

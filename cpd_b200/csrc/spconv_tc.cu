@@ -101,7 +101,7 @@ struct TcArgs {
     int cin, K, cout, relu;
     int cin_shift;              // log2(cin) when cin is a power of two (every CPD layer), else -1
     int l2_hints;               // gathers with L2 evict_last, table slices with evict_first (CPD_L2_HINTS; measured neutral, default off)
-    int debug;                  // CPD_TC_DEBUG (timing experiments only, results are WRONG): 1 = no zero-fill copies, 2 = no MMAs, 4 = no epilogue stores
+    int debug;                  // CPD_TC_DEBUG (timing experiments only, results are WRONG): 1 = no zero-fill copies, 2 = no MMAs, 4 = no epilogue stores, 8 = no B-tile reloads
 };
 
 // DENSE variant (cpd_conv2d_fwd / cpd_conv2d_dgrad: the dense BEV convolutions, stride 1): the rows of an output tile are a
@@ -523,10 +523,12 @@ __global__ void __launch_bounds__(DENSE ? NTHREADS_DENSE : NTHREADS_SP, 1) gathe
                         mbar_arrive_expect_tx(full0 + 8 * s, tile_bytes + 2 * A_BYTES);
                         tma_load_4d(stage_u32, &xmap, full0 + 8 * s, ch, x0 + kx, y0 + ky, img);
                         tma_load_4d(stage_u32 + A_BYTES, &xmap, full0 + 8 * s, a.cin + ch, x0 + kx, y0 + ky, img);
+                    } else if ((a.debug & 8) && g >= STAGES) {      // (timing experiment: B tiles are loaded once per stage only)
+                        mbar_arrive(full0 + 8 * s);
                     } else {
                         mbar_arrive_expect_tx(full0 + 8 * s, tile_bytes);
                     }
-                    bulk_copy_g2s(stage_u32 + 2 * A_BYTES, src, tile_bytes, full0 + 8 * s);
+                    if (DENSE || !((a.debug & 8) && g >= STAGES)) bulk_copy_g2s(stage_u32 + 2 * A_BYTES, src, tile_bytes, full0 + 8 * s);
                 }
                 __syncwarp();
                 ++g;

@@ -73,6 +73,8 @@ class Rulebook:
         key = (which, tpb)
         if key not in self._sorted:
             keys = ops.tap_block_keys(nb, tpb)
+            if (27 + tpb - 1) // tpb <= 15:                      # <= 15 key bits: half the radix passes on an int16 key
+                keys = keys.to(torch.int16)
             perm = torch.sort(keys, stable=True)[1]              # stable: spatial locality survives inside a group
             nbs = nb.index_select(0, perm)
             self._sorted[key] = (nbs, perm.to(torch.int32), ops.tile_tap_masks(nbs))
