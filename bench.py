@@ -316,6 +316,7 @@ def run_ours(a):
         # ---- timed region: K steps, inputs resident in HBM, L2 flushed between steps ----
         l0 = _lib.launch_count()
         evs = []
+        alloc_trace = []
         barrier()
         for i in range(a.steps):
             flush.zero_()
@@ -324,12 +325,19 @@ def run_ours(a):
             res, enc = run_resident(i)
             e1.record()
             evs.append((e0, e1))
+            ms_ = torch.cuda.memory_stats(dev)
+            alloc_trace.append((ms_.get("reserved_bytes.all.current", 0), ms_.get("num_device_alloc", 0), ms_.get("num_device_free", 0),
+                                ms_.get("num_alloc_retries", 0), time.perf_counter()))
         barrier()
         launches = _lib.launch_count() - l0
         if train and not a.no_graph:            # kernels replayed from the captured graphs do not pass through the library's counter
             launches += net.dense_graph_launches * a.steps
         step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
         total_ms = sum(step_ms)
+        if os.environ.get("CPD_BENCH_DIAG"):          # which steps grew the allocator / how long the host took to enqueue them
+            for i, (rb_, na, nf, nr, tp) in enumerate(alloc_trace):
+                sys.stderr.write(f"[diag] step {i}: {step_ms[i]:7.2f} ms  reserved {rb_ / 1e9:6.2f} GB  device allocs {na} frees {nf} retries {nr}  "
+                                 f"host dt {1e3 * (tp - (alloc_trace[i - 1][4] if i else tp)):7.2f} ms\n")
         # ---- roofline pass: the same K steps again with CUDA events around every gather-GEMM / wgrad launch
         #      (per-launch events perturb the step, so `value` above comes from the clean pass) ----
         ops.PROFILE = []

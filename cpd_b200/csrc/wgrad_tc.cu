@@ -78,7 +78,7 @@ struct WgArgs {
     float *dw;
     long long m_out;
     int cin, cout, K, rows_per_cta, ci_tiles, taps_per_group;
-    int l2_hints;                // gathers with L2 evict_last (CPD_L2_HINTS, default on)
+    int skip_zero;               // skip the zero-fill copy of slots that are already zero (CPD_WGRAD_SKIP_ZERO, default on)
 };
 
 template <int BN, int AM>
@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
         const uint32_t tiles_u32 = smem_u32(tiles);
         const size_t dy_row = (size_t)a.cout * 4;                                  // image rows: hi(c) | lo(c)
         const uint32_t x_row32 = (uint32_t)a.cin * 4, nbr_w_u32 = smem_u32(nbr_w);
-        const uint64_t pol_keep = l2_policy_evict_last();
+        uint32_t bstate = 0u;                       // bit (stage * B_V + j): this thread's slot j of the stage holds gathered data
+        static_assert(w_stages(BN, AM) * B_V <= 32, "slot-state bits");
         const uint32_t x_lo = (uint32_t)a.cin * 2, dy_lo = (uint32_t)a.cout * 2;
 
         // ---- neighbour-table windows (T x 128 entries): fetched into registers two windows ahead, published into
@@ -201,19 +202,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) gather_wgrad_rows_kernel(WgArgs a
                 cp_async16(dst + A_BYTES + a_off[j], src + dy_lo, ok ? 16u : 0u);
             }
             if (b_live) {
+                // 40-85 % of the (row, tap) slots have no neighbour.  All stages start zeroed, so a missing neighbour needs a
+                // zero-fill copy only when the slot still holds data from the stage's previous use (bstate: one bit per
+                // (stage, row of this thread)): the copies -- the LSU / shared-memory wavefronts that bound this kernel --
+                // drop from one per slot to one per present slot + one per data -> empty transition.
                 const uint8_t *col_hi = a.xs + (size_t)b_ci * 2, *col_lo = col_hi + x_lo;
+                const uint32_t held = (bstate >> (s * B_V)) & ((1u << B_V) - 1u);
+                uint32_t now = 0u;
 #pragma unroll
                 for (int j = 0; j < B_V; ++j) {
-                    const uint32_t sz = idx[j] >= 0 ? 16u : 0u;
-                    const uint64_t off = (uint64_t)(uint32_t)max(idx[j], 0) * x_row32;
-                    if (a.l2_hints) {
-                        cp_async16_hint(dst + 2 * A_BYTES + b_off[j], col_hi + off, sz, pol_keep);
-                        cp_async16_hint(dst + 2 * A_BYTES + B_BYTES + b_off[j], col_lo + off, sz, pol_keep);
-                    } else {
+                    const bool present = idx[j] >= 0;
+                    if (present || ((held >> j) & 1u) || !a.skip_zero) {
+                        const uint32_t sz = present ? 16u : 0u;
+                        const uint64_t off = (uint64_t)(uint32_t)max(idx[j], 0) * x_row32;
                         cp_async16(dst + 2 * A_BYTES + b_off[j], col_hi + off, sz);
                         cp_async16(dst + 2 * A_BYTES + B_BYTES + b_off[j], col_lo + off, sz);
                     }
+                    now |= (present ? 1u : 0u) << j;
                 }
+                bstate = (bstate & ~(((1u << B_V) - 1u) << (s * B_V))) | (now << (s * B_V));
             }
         };
         // before block `blk` is ISSUED its window's table must be published; windows are 4 blocks long
@@ -423,8 +430,8 @@ int32_t gather_wgrad_rows_tc(const void *xs, int32_t cin, const void *dys, int64
     long long rows = div_up(div_up(m_out, S), WINR) * WINR;
     S = div_up(m_out, rows);
     CPD_REQUIRE(S <= 65535, CPD_ERR_UNSUPPORTED, "tcgen05 wgrad: too many row slices");
-    static const int l2_hints = getenv("CPD_L2_HINTS") ? atoi(getenv("CPD_L2_HINTS")) : 0;
-    WgArgs a{reinterpret_cast<const uint8_t *>(xs), reinterpret_cast<const uint8_t *>(dys), nbr_t, dw, m_out, cin, cout, K, (int)rows, ci_tiles, tpg, l2_hints};
+    static const int skip_zero = getenv("CPD_WGRAD_SKIP_ZERO") ? atoi(getenv("CPD_WGRAD_SKIP_ZERO")) : 1;
+    WgArgs a{reinterpret_cast<const uint8_t *>(xs), reinterpret_cast<const uint8_t *>(dys), nbr_t, dw, m_out, cin, cout, K, (int)rows, ci_tiles, tpg, skip_zero};
     dim3 grid(groups, (unsigned)S, ci_tiles * co_tiles);
     if (bn == 256) return launch_wg_am<256>(am, a, grid, stream);
     return launch_wg_am<128>(am, a, grid, stream);
