@@ -176,7 +176,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 self.rows.append([t.strip() for t in line.split(",")])
         except Exception:
@@ -219,6 +219,15 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # each rank runs a launching thread, an autograd thread and NCCL's proxy: give every rank its own slice of the host's
+        # cores instead of letting 8 x 3 busy threads migrate over all of them (the step is host-paced when they collide)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = len(cores) // world
+            if per >= 2:
+                os.sched_setaffinity(0, cores[local * per:(local + 1) * per])
+        except (AttributeError, OSError):
+            pass
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
     train = a.workload == "detector_train"
@@ -301,7 +310,8 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:                                  # one nvidia-smi poller per job (rank 0's GPU), at the recipe's 200 ms period: every
+        sampler.start()                            # query takes driver locks that the launching threads of ALL ranks contend for
     # Python's cyclic garbage collector is driven by hand, as training loops at scale do (a generation-2 pass over the
     # autograd / rulebook object graph takes 10-30 ms of host time and showed up as isolated 54-78 ms steps): collected
     # between the phases below, never inside a timed step.
@@ -372,7 +382,7 @@ def run_ours(a):
             d2h = out.numel() * 4
         barrier()
         e2e_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs2)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
 
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:

@@ -27,6 +27,8 @@ SIGNATURES = {
     "cpd_split_rows": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "cpd_tile_tap_masks": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "cpd_tap_block_keys": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),
+    "cpd_table_permute": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "cpd_table_transpose": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "cpd_gather_gemm": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
     "cpd_gather_gemm_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32, _i32, _i32, _i32]),
     "cpd_gather_wgrad": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),

@@ -242,6 +242,58 @@ inline GeoClass geo_class(const Ker &k)
         }                                                                                                                     \
     } while (0)
 
+// ---- table post-processing (what torch's index_select / .to(int32) / .t().contiguous() did in 3 + 1 strided passes) ----
+constexpr int TT_ROWS = 128;     // rows per CTA = one tile of the tensor-core kernels
+
+// out[r, :] = nbr[perm[r], :], out_rows[r] = perm[r], masks[tile] = taps present anywhere in the tile.
+// 128 threads; the K entries of a source row are read by consecutive lanes, the 128 x K block is written back contiguously.
+__global__ void __launch_bounds__(TT_ROWS) table_permute_kernel(const int32_t *__restrict__ nbr, long long m, int K,
+                                                                  const long long *__restrict__ perm, int32_t *__restrict__ out,
+                                                                  int32_t *__restrict__ out_rows, uint32_t *__restrict__ masks)
+{
+    extern __shared__ int32_t tt_s[];            // [TT_ROWS * K] + [TT_ROWS] source rows
+    int32_t *src_row = tt_s + TT_ROWS * K;
+    __shared__ uint32_t acc;
+    const long long r0 = (long long)blockIdx.x * TT_ROWS;
+    const int rows = (int)min((long long)TT_ROWS, m - r0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) acc = 0u;
+    if (tid < rows) {
+        const long long p = perm[r0 + tid];
+        src_row[tid] = (int32_t)p;
+        out_rows[r0 + tid] = (int32_t)p;
+    }
+    __syncthreads();
+    uint32_t mine = 0u;
+    for (int r = warp; r < rows; r += TT_ROWS / 32) {             // one warp per source row: K <= 32 consecutive words
+        if (lane < K) {
+            const int32_t v = __ldg(nbr + (long long)src_row[r] * K + lane);
+            tt_s[r * K + lane] = v;
+            if (v >= 0) mine |= 1u << lane;
+        }
+    }
+    mine = __reduce_or_sync(0xffffffffu, mine);
+    if (lane == 0 && mine) atomicOr(&acc, mine);
+    __syncthreads();
+    for (int e = tid; e < rows * K; e += TT_ROWS) out[r0 * K + e] = tt_s[e];
+    if (tid == 0 && masks) masks[blockIdx.x] = acc;
+}
+
+// nbr (m, K) -> nbr_t (K, m): coalesced on both sides through a shared-memory tile of 128 rows.
+__global__ void __launch_bounds__(TT_ROWS) table_transpose_kernel(const int32_t *__restrict__ nbr, long long m, int K,
+                                                                    int32_t *__restrict__ nbr_t)
+{
+    extern __shared__ int32_t tt_s[];            // [TT_ROWS][K + 1]  (odd pitch when K is even: column reads stay conflict-free)
+    const int pitch = K | 1;
+    const long long r0 = (long long)blockIdx.x * TT_ROWS;
+    const int rows = (int)min((long long)TT_ROWS, m - r0);
+    const int tid = threadIdx.x;
+    for (int e = tid; e < rows * K; e += TT_ROWS) tt_s[(e / K) * pitch + e % K] = __ldg(nbr + r0 * K + e);
+    __syncthreads();
+    if (tid < rows)
+        for (int k = 0; k < K; ++k) nbr_t[(long long)k * m + r0 + tid] = tt_s[tid * pitch + k];
+}
+
 int32_t make_geo(const int32_t *shape3, int32_t batch, Geo *g, const char *who)
 {
     CPD_REQUIRE(shape3 && batch >= 1, CPD_ERR_BAD_ARG, "%s: bad shape/batch", who);
@@ -405,4 +457,26 @@ extern "C" int32_t cpd_rulebook_strided_tables(const int32_t *in_coords, int64_t
         }
     }
     return launch_status("cpd_rulebook_strided_tables");
+}
+
+extern "C" int32_t cpd_table_permute(const int32_t *nbr, int64_t m, int32_t K, const int64_t *perm, int32_t *out_nbr,
+                                     int32_t *out_rows, uint32_t *tile_masks, cpd_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CPD_REQUIRE(nbr && perm && out_nbr && out_rows && m >= 0 && K >= 1 && K <= 32, CPD_ERR_BAD_ARG, "cpd_table_permute: bad argument (1 <= K <= 32)");
+    if (m == 0) return CPD_OK;
+    table_permute_kernel<<<(unsigned)div_up(m, TT_ROWS), TT_ROWS, (size_t)(TT_ROWS * K + TT_ROWS) * 4, stream>>>(
+        nbr, m, K, reinterpret_cast<const long long *>(perm), out_nbr, out_rows, tile_masks);
+    count_launch();
+    return launch_status("cpd_table_permute");
+}
+
+extern "C" int32_t cpd_table_transpose(const int32_t *nbr, int64_t m, int32_t K, int32_t *nbr_t, cpd_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CPD_REQUIRE(nbr && nbr_t && m >= 0 && K >= 1 && K <= 64, CPD_ERR_BAD_ARG, "cpd_table_transpose: bad argument (1 <= K <= 64)");
+    if (m == 0) return CPD_OK;
+    table_transpose_kernel<<<(unsigned)div_up(m, TT_ROWS), TT_ROWS, (size_t)TT_ROWS * (K | 1) * 4, stream>>>(nbr, m, K, nbr_t);
+    count_launch();
+    return launch_status("cpd_table_transpose");
 }

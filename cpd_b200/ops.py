@@ -258,6 +258,30 @@ def tap_block_keys(nbr, taps_per_block):
     return keys
 
 
+def table_permute(nbr, perm, want_masks=True):
+    """(nbr[perm], perm as int32, tile tap masks of the permuted table) in one pass over the table."""
+    _need_cuda(nbr, perm)
+    L = _lib.lib()
+    m, K = nbr.shape
+    assert perm.dtype == torch.int64 and perm.numel() == m and perm.is_contiguous() and nbr.is_contiguous()
+    out = torch.empty_like(nbr)
+    rows = torch.empty((m,), dtype=torch.int32, device=nbr.device)
+    masks = torch.empty(((m + 127) // 128,), dtype=torch.int32, device=nbr.device) if want_masks else None
+    _lib.check(L.cpd_table_permute(_ptr(nbr), m, K, _ptr(perm), _ptr(out), _ptr(rows), _ptr(masks), _stream()), "cpd_table_permute")
+    return out, rows, masks
+
+
+def table_transpose(nbr):
+    """(m, K) neighbour table -> tap-major (K, m) (the layout cpd_gather_wgrad reads)."""
+    _need_cuda(nbr)
+    L = _lib.lib()
+    m, K = nbr.shape
+    assert nbr.dtype == torch.int32 and nbr.is_contiguous()
+    out = torch.empty((K, m), dtype=torch.int32, device=nbr.device)
+    _lib.check(L.cpd_table_transpose(_ptr(nbr), m, K, _ptr(out), _stream()), "cpd_table_transpose")
+    return out
+
+
 def gather_gemm(x, w, nbr, bias=None, scale=None, shift=None, residual=None, relu=False, stats=None,
                 algo=ALGO_AUTO, out=None, x_split=None, tile_masks=None, out_rows=None):
     """y[o] = epi(sum_k W[:,k,:] x[nbr[o,k]]);  w is (cout, K, cin) (any (cout, ..., cin) view).

@@ -42,7 +42,8 @@ class Rulebook:
     @property
     def nbr_fwd_t(self):
         if self._nbr_fwd_t is None:
-            self._nbr_fwd_t = self.nbr_fwd.t().contiguous()
+            nb = self.nbr_fwd
+            self._nbr_fwd_t = ops.table_transpose(nb) if (nb.is_cuda and nb.shape[1] <= 64 and nb.shape[0] > 0) else nb.t().contiguous()
         return self._nbr_fwd_t
 
     @property
@@ -76,8 +77,7 @@ class Rulebook:
             if (27 + tpb - 1) // tpb <= 15:                      # <= 15 key bits: half the radix passes on an int16 key
                 keys = keys.to(torch.int16)
             perm = torch.sort(keys, stable=True)[1]              # stable: spatial locality survives inside a group
-            nbs = nb.index_select(0, perm)
-            self._sorted[key] = (nbs, perm.to(torch.int32), ops.tile_tap_masks(nbs))
+            self._sorted[key] = ops.table_permute(nb, perm)      # (sorted table, its rows as int32, tile masks) in one pass
         return self._sorted[key]
 
     def bwd_sorted(self, channels=64):

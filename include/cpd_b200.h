@@ -156,6 +156,14 @@ CPD_API int32_t cpd_tile_tap_masks(const int32_t *nbr, int64_t m, int32_t K, uin
  * through cpd_gather_gemm's out_rows.  ceil(K / taps_per_block) <= 31. */
 CPD_API int32_t cpd_tap_block_keys(const int32_t *nbr, int64_t m, int32_t K, int32_t taps_per_block, int32_t *keys, cpd_stream_t stream);
 
+/* The sorted table in one pass: out_nbr[r, :] = nbr[perm[r], :], out_rows[r] = (int32) perm[r], tile_masks[t] (NULL ok) as
+ * cpd_tile_tap_masks(out_nbr).  perm: int64 permutation of [0, m) (the argsort of cpd_tap_block_keys).  K <= 32. */
+CPD_API int32_t cpd_table_permute(const int32_t *nbr, int64_t m, int32_t K, const int64_t *perm, int32_t *out_nbr,
+                                  int32_t *out_rows, uint32_t *tile_masks, cpd_stream_t stream);
+
+/* nbr (m, K) -> nbr_t (K, m): the tap-major table cpd_gather_wgrad reads (tap_major = 1).  K <= 64. */
+CPD_API int32_t cpd_table_transpose(const int32_t *nbr, int64_t m, int32_t K, int32_t *nbr_t, cpd_stream_t stream);
+
 /* x_split (NULL ok): split-row image of x (cpd_split_rows); have_x_split tells the workspace query
  * whether the call will pass one.  tile_masks (NULL ok): cpd_tile_tap_masks(nbr).
  * out_rows (NULL ok, tensor-core kernel only): a permutation of [0, m_out); row r of the table is written to

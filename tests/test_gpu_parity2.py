@@ -260,3 +260,23 @@ def test_detector_train_step_matches_cpu_port(cuda):
         worst = max(worst, rc / max(rp, 1e-7))
         print(f"  {key:34s} rel L2: cuda vs port {rc:.2e}   port(2^-17 noise) vs port {rp:.2e}   ratio {rc / max(rp, 1e-7):.2f}")
     assert worst <= 8.0, worst
+
+
+@pytest.mark.parametrize("m,K", [(1, 27), (127, 27), (128, 27), (5000, 27), (70001, 27), (300, 9), (513, 3), (1000, 32), (777, 1)])
+def test_table_permute_and_transpose_match_torch(cuda, m, K):
+    """cpd_table_permute == (index_select by the permutation, int32 rows, cpd_tile_tap_masks of the result) and
+    cpd_table_transpose == .t().contiguous(): integer work, bit-exact."""
+    from cpd_b200 import ops
+    g = torch.Generator().manual_seed(m * 31 + K)
+    nbr = torch.randint(-1, max(m, 2), (m, K), generator=g, dtype=torch.int32)
+    nbr[torch.rand(m, K, generator=g) < 0.5] = -1
+    if m > 256:
+        nbr[128:256, : max(1, K // 2)] = -1                     # a tile that lacks whole taps
+    nbr = nbr.to(cuda)
+    perm = torch.randperm(m, generator=g).to(cuda)
+    out, rows, masks = ops.table_permute(nbr, perm)
+    ref = nbr.index_select(0, perm)
+    assert torch.equal(out, ref) and torch.equal(rows, perm.to(torch.int32))
+    assert torch.equal(masks, ops.tile_tap_masks(ref))
+    t = ops.table_transpose(nbr)
+    assert t.shape == (K, m) and torch.equal(t, nbr.t().contiguous())
