@@ -323,6 +323,17 @@ def run_ours(a):
             run_resident(i)
         barrier()
         gc.collect()
+        if train:
+            # Pre-size the caching allocator: the two batches of the pool differ in size, so the pools of both streams keep
+            # growing by a few tens of MB for ~25 steps (cuMemCreate / cuMemMap under expandable segments), and such a growth
+            # inside a timed step was seen to stall it for 10-280 ms.  Allocating and releasing headroom once leaves it
+            # cached (mapped) in each stream's pool.
+            for st in (torch.cuda.current_stream(dev), getattr(net, "_side", None)):
+                if st is not None:
+                    with torch.cuda.stream(st):
+                        pad = [torch.empty(1 << 30, dtype=torch.uint8, device=dev) for _ in range(3)]
+                        del pad
+            barrier()
         # ---- timed region: K steps, inputs resident in HBM, L2 flushed between steps ----
         l0 = _lib.launch_count()
         evs = []
@@ -497,7 +508,10 @@ def run_ours(a):
                    "active_voxels_last_batch": int(enc.indices.shape[0])},
         "e2e": {"value": frames_total / (e2e_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
-        "gpu_launches": int(launches), "peak_hbm_gb_rank0": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2), "clocks": clocks, "roofline": roof, "front_end": front_end,
+        "gpu_launches": int(launches),
+        "allocator_rank0": {"device_allocs_during_timed_steps": int(alloc_trace[-1][1] - alloc_trace[0][1]) if alloc_trace else None,
+                            "reserved_gb": round(alloc_trace[-1][0] / 1e9, 2) if alloc_trace else None},
+        "peak_hbm_gb_rank0": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2), "clocks": clocks, "roofline": roof, "front_end": front_end,
         "sparse_levels": sorted(stages.values(), key=lambda d: -d["rows"]),
     }
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

@@ -379,27 +379,39 @@ def assign_targets_single(gt_boxes, num_classes, fmap_xy, stride, pc_range, voxe
 
 
 def assign_targets_batched(gt_boxes, num_classes, fmap_xy, stride, pc_range, voxel_size, num_max_objs=500,
-                           gaussian_overlap=0.1, min_radius=2, max_radius=24):
-    """assign_targets_single over a whole batch at once: gt_boxes (B, M, 8) -> heatmap (B, C, H, W), ret_boxes
-    (B, num_max_objs, 8), inds / mask (B, num_max_objs).  Same arithmetic, one set of launches instead of one per frame
-    (the forward pass is host-bound, every launch counts); the frame index is folded into the scatter index."""
+                           gaussian_overlap=0.1, min_radius=2, max_radius=24, strict=False):
+    """center_head.py:103-157,188-207 over a whole batch at once: gt_boxes (B, M, 8+) with the HEAD-LOCAL class in the last
+    column (0 = not in this head / padding) -> heatmap (B, C, H, W), ret_boxes (B, num_max_objs, 8+), inds / mask
+    (B, num_max_objs).  Same arithmetic as assign_targets_single, one set of launches instead of one per frame; the frame index
+    is folded into the scatter index.
+    Like the reference, the boxes of the head are COMPACTED first (stable) and then the first num_max_objs of them are used, so
+    slot k of ret_boxes / inds / mask is the k-th box of this head, also with several heads or more than num_max_objs rows;
+    extra box columns (velocity, gt[..., 7:-1]) are carried into ret_boxes[..., 8:].
+    The one deliberate bound: a gaussian is rasterised into a (2 max_radius + 1)^2 patch, so radii are exact up to max_radius
+    (24 feature-map pixels = a 19 m object at stride 8 x 0.1 m; the reference has no cap).  strict=True checks it (one host sync)."""
     W, H = int(fmap_xy[0]), int(fmap_xy[1])
     dev = gt_boxes.device
-    gt = gt_boxes[:, :num_max_objs]
-    B, m = gt.shape[0], gt.shape[1]
-    heatmap = gt.new_zeros(B, num_classes, H, W)
-    ret_boxes = gt.new_zeros((B, num_max_objs, 8))
+    B, ncol = gt_boxes.shape[0], gt_boxes.shape[-1]
+    heatmap = gt_boxes.new_zeros(B, num_classes, H, W)
+    ret_boxes = gt_boxes.new_zeros((B, num_max_objs, ncol))
     inds = torch.zeros((B, num_max_objs), dtype=torch.long, device=dev)
     mask = torch.zeros((B, num_max_objs), dtype=torch.long, device=dev)
-    if m == 0 or B == 0:
+    if gt_boxes.shape[1] == 0 or B == 0:
         return heatmap, ret_boxes, inds, mask
+    in_head = (gt_boxes[..., -1] >= 1) & (gt_boxes[..., -1] <= num_classes)
+    order = torch.sort((~in_head).to(torch.int8), dim=1, stable=True)[1]          # this head's boxes first, original order kept
+    gt = torch.gather(gt_boxes, 1, order[..., None].expand(-1, -1, ncol))[:, :num_max_objs]
+    in_head = torch.gather(in_head, 1, order)[:, :num_max_objs]
+    m = gt.shape[1]
     cx = ((gt[..., 0] - pc_range[0]) / voxel_size[0] / stride).clamp(min=0, max=W - 0.5)
     cy = ((gt[..., 1] - pc_range[1]) / voxel_size[1] / stride).clamp(min=0, max=H - 0.5)
     ix, iy = cx.int(), cy.int()
     dx, dy = gt[..., 3] / voxel_size[0] / stride, gt[..., 4] / voxel_size[1] / stride
     radius = torch.clamp_min(gaussian_radius(dx, dy, min_overlap=gaussian_overlap).int(), min_radius)
-    cls = gt[..., 7].long() - 1
-    valid = (dx > 0) & (dy > 0) & (cls >= 0) & (cls < num_classes)
+    cls = gt[..., -1].long() - 1
+    valid = (dx > 0) & (dy > 0) & in_head
+    if strict:
+        assert int(torch.where(valid, radius, torch.zeros_like(radius)).max()) <= max_radius, "gaussian radius exceeds max_radius"
     radius = radius.clamp(max=max_radius)
     R = max_radius
     off = torch.arange(-R, R + 1, device=dev)
@@ -419,6 +431,8 @@ def assign_targets_batched(gt_boxes, num_classes, fmap_xy, stride, pc_range, vox
     mask[:, :m] = v
     rb = torch.stack([cx - ix.float(), cy - iy.float(), gt[..., 2], gt[..., 3].clamp_min(1e-6).log(), gt[..., 4].clamp_min(1e-6).log(),
                       gt[..., 5].clamp_min(1e-6).log(), torch.cos(gt[..., 6]), torch.sin(gt[..., 6])], dim=2)
+    if ncol > 8:
+        rb = torch.cat([rb, gt[..., 7:-1]], dim=2)
     ret_boxes[:, :m] = rb * valid[..., None].float()
     return heatmap, ret_boxes, inds, mask
 

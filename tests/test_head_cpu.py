@@ -77,3 +77,34 @@ def test_batched_target_assignment_equals_per_frame():
     assert float(e[0].abs().sum()) == 0 and int(e[3].sum()) == 0 and tuple(e[0].shape) == (3, 3, 188, 188)
     capped = bev.assign_targets_batched(gt, 3, [188, 188], 8, RANGE, VS, num_max_objs=7)
     assert tuple(capped[1].shape) == (3, 7, 8) and int(capped[3].sum()) <= 21
+
+
+def test_multi_head_targets_compact_per_head_like_the_reference():
+    """center_head.py:188-207: each head first collects ITS boxes (order kept, class made head-local), then the first
+    NUM_MAX_OBJS of them fill slots 0, 1, ... -- also when other heads' boxes and padding rows sit in between, when there are
+    more boxes than slots, and with extra (velocity) columns.  Compared with the per-frame routine on hand-compacted boxes."""
+    torch.manual_seed(5)
+    names = ["Vehicle", "Pedestrian", "Cyclist"]
+    cfg = dict(bev.DEFAULT_HEAD_CFG)
+    cfg["CLASS_NAMES_EACH_HEAD"] = [["Vehicle", "Cyclist"], ["Pedestrian"]]
+    cfg["TARGET_ASSIGNER_CONFIG"] = dict(cfg["TARGET_ASSIGNER_CONFIG"], NUM_MAX_OBJS=9)
+    head = bev.CenterHead(cfg, 1, 512, 3, names, [1504, 1504, 40], RANGE, VS)
+    gt0 = torch.from_numpy(G["gt"])[:24].clone()
+    gt0[:, 7] = torch.tensor([1, 2, 3, 0, 2, 1, 1, 3, 0, 2, 3, 1] * 2, dtype=gt0.dtype)      # interleaved classes and padding
+    gt = torch.stack([gt0, gt0.flip(0).clone()], 0)
+    gt10 = torch.cat([gt[..., :7], torch.randn(2, 24, 2), gt[..., 7:]], -1)                    # + (vx, vy) before the class
+    for g in (gt, gt10):
+        ret = head.assign_targets(g, (188, 188))
+        for h, local_names in enumerate(cfg["CLASS_NAMES_EACH_HEAD"]):
+            for b in range(2):
+                rows = [r.clone() for r in g[b] if int(r[-1]) >= 1 and names[int(r[-1]) - 1] in local_names]
+                for r in rows:
+                    r[-1] = local_names.index(names[int(r[-1]) - 1]) + 1
+                sel = torch.stack(rows)[:9]
+                sel8 = torch.cat([sel[:, :7], sel[:, -1:]], 1)
+                hm, rb, inds, mask = bev.assign_targets_single(sel8, len(local_names), [188, 188], 8, RANGE, VS, 9, 0.1, 2)
+                assert torch.equal(ret["heatmaps"][h][b], hm) and torch.equal(ret["inds"][h][b], inds) and torch.equal(ret["masks"][h][b], mask)
+                assert torch.equal(ret["target_boxes"][h][b][:, :8], rb)
+                if g.shape[-1] > 8:
+                    assert torch.equal(ret["target_boxes"][h][b][:len(sel), 8:], sel[:, 7:-1] * mask[:len(sel), None])
+                assert int(mask.sum()) > 0
