@@ -195,7 +195,7 @@ class CPDHotPathDetector(nn.Module):
             loss, tb = self.dense_head.get_loss()
             if self.roi_pool is not None:
                 # RoI grid pooling on both towers (voxel_rcnn_head.py:186-343): the real consumer of x_conv3 / x_conv4
-                rois = bd["rois"][:, :self.rois_per_image, :7].detach()
+                rois = bd["rois"][:, :self.rois_per_image, :7].detach().contiguous()
                 strides = bd["multi_scale_3d_strides"]
                 pooled = self.roi_pool(rois, bd["multi_scale_3d_features"], strides)
                 tb["roi_pooled_abs_mean"] = pooled.detach().abs().mean()

@@ -35,13 +35,13 @@ def get_voxel_centers(voxel_coords, downsample_times, voxel_size, point_cloud_ra
 def get_dense_grid_points(rois, batch_size_rcnn, grid_size):
     """voxel_rcnn_head.py:377-386."""
     dense_idx = rois.new_ones((grid_size, grid_size, grid_size)).nonzero().repeat(batch_size_rcnn, 1, 1).float()
-    size = rois.view(batch_size_rcnn, -1)[:, 3:6]
+    size = rois.reshape(batch_size_rcnn, -1)[:, 3:6]
     return (dense_idx + 0.5) / grid_size * size.unsqueeze(1) - size.unsqueeze(1) / 2
 
 
 def get_global_grid_points_of_roi(rois, grid_size):
     """voxel_rcnn_head.py:365-375."""
-    rois = rois.view(-1, rois.shape[-1])
+    rois = rois.reshape(-1, rois.shape[-1])
     local = get_dense_grid_points(rois, rois.shape[0], grid_size)
     glob = rotate_points_along_z(local.clone(), rois[:, 6]).squeeze(1) + rois[:, 0:3].unsqueeze(1)
     return glob, local
