@@ -54,6 +54,28 @@ def _gather_gemm(x, w, nbr, bias=None, scale=None, shift=None, residual=None, re
     return y.float()
 
 
+def _weight_transpose(w, flip_taps=False):
+    cout, cin = w.shape[0], w.shape[-1]
+    w = w.detach().reshape(cout, -1, cin)
+    if flip_taps:
+        w = w.flip(1)
+    return w.permute(2, 1, 0).contiguous()
+
+
+def _gather_wgrad(x, dy, nbr, want_bias=False, algo=0, tap_major=False, x_split=None, dy_split=None):
+    if tap_major:
+        nbr = nbr.t()
+    xd, dyd = x.detach().double(), dy.detach().double()
+    K = nbr.shape[1]
+    dw = torch.zeros((dy.shape[1], K, x.shape[1]), dtype=torch.float64)
+    for k in range(K):
+        idx = nbr[:, k].long()
+        ok = idx >= 0
+        if bool(ok.any()):
+            dw[:, k, :] = dyd[ok].t() @ xd[idx[ok]]
+    return dw.float(), (dyd.sum(0).float() if want_bias else None)
+
+
 def _dense(feat, coords, batch, shape, channels_last=False):
     d = torch.from_numpy(O.dense(feat.detach().numpy(), coords.numpy(), batch, list(shape)))
     if channels_last:
@@ -65,7 +87,7 @@ def _dense(feat, coords, batch, shape, channels_last=False):
 @contextlib.contextmanager
 def cpu_ops():
     saved = {k: getattr(ops, k) for k in ("build_hash", "subm_table", "strided_outputs", "strided_tables", "gather_gemm", "tile_tap_masks",
-                                          "split_rows", "sparse_to_dense")}
+                                          "split_rows", "sparse_to_dense", "gather_wgrad", "weight_transpose")}
     saved_min = sparse.Rulebook.SORT_MIN_ROWS
 
     def strided_outputs(coords, shape, batch, ksize, stride, padding):
@@ -82,6 +104,7 @@ def cpu_ops():
         _fwd_table(O.rulebook_subm(coords.numpy(), list(shape), ksize), coords.shape[0]))
     ops.strided_outputs, ops.strided_tables = strided_outputs, strided_tables
     ops.gather_gemm = _gather_gemm
+    ops.gather_wgrad, ops.weight_transpose = _gather_wgrad, _weight_transpose
     ops.tile_tap_masks = lambda nbr: torch.zeros(((nbr.shape[0] + 127) // 128,), dtype=torch.int32)
     ops.split_rows = lambda x, colsum=False: (None, None) if colsum else None
     ops.sparse_to_dense = _dense
