@@ -255,7 +255,8 @@ def run_ours(a):
             net.capture_dense_graph(a.batch)                       # static-shape part of the step: forward + backward as CUDA graphs
         model = net
         if world > 1:
-            model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local])
+            ddp_kw = json.loads(os.environ.get("CPD_DDP_KWARGS", "{}"))           # experiments: {"broadcast_buffers": false, ...}
+            model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], **ddp_kw)
         opt = torch.optim.Adam(net.parameters(), lr=1e-4, fused=True)
 
         pending = {}                                               # input stage of the NEXT step, already enqueued on a side stream
