@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--prefetch", action="store_true", help="(default) run the input stage (voxelize + rulebooks) one step ahead on a side "
                                                             "stream (detector.prepare), like a prefetching DataLoader")
     ap.add_argument("--no-prefetch", action="store_true", help="run the input stage inline at the start of every forward")
+    ap.add_argument("--prefetch-thread", action="store_true", help="run the prefetched input stage on a worker thread (detector.prepare_async), "
+                                                                   "submitted at the START of the step before")
     a = ap.parse_args()
     if a.workload == "stress" and a.points == 160000:
         a.points = 300000                      # BASELINE configs[4]: 300k points / 200k active voxels per frame
@@ -171,7 +173,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.rows, self.gpu, self.proc = [], gpu_index, None
+        self.rows, self.gpu, self.proc, self.first = [], gpu_index, None, 0
 
     def run(self):
         try:
@@ -182,12 +184,21 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
+    def mark(self):
+        """Statistics are taken over the samples from here on (the timed phases), not over the idle set-up."""
+        self.first = len(self.rows)
+
+    def wait_first(self, timeout):
+        t0 = time.perf_counter()
+        while not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=2)
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[1])); mx = max(mx, float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -230,6 +241,9 @@ def run_ours(a):
             pass
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
+    sampler = ClockSampler(local)
+    if rank == 0:                                  # one nvidia-smi poller per job (rank 0's GPU), at the recipe's 200 ms period: every
+        sampler.start()                            # query takes driver locks that the launching threads of ALL ranks contend for
     train = a.workload == "detector_train"
     if a.workload == "stress":
         a.pool = 1                                 # generating a 200k-voxel scene takes seconds: one batch, L2 flushed between steps
@@ -274,10 +288,13 @@ def run_ours(a):
             prep = pending.pop((id(src), i), None)
             if prep is None or a.no_prefetch:
                 prep = None if a.no_prefetch else net.prepare(mk(i))
+            if a.prefetch_thread and not a.no_prefetch:            # step i+1's input stage: a worker thread, the whole step to finish
+                pending.clear()
+                pending[(id(src), i + 1)] = net.prepare_async(mk(i + 1))
             loss, tb = model(mk(i), prepared=prep)
             opt.zero_grad(set_to_none=True)
             loss.backward()                                        # DDP: NCCL all-reduce of the gradients overlaps here
-            if not a.no_prefetch:                                  # like a prefetching DataLoader: H2D + voxelize + rulebooks of step i+1
+            if not a.no_prefetch and not a.prefetch_thread:        # like a prefetching DataLoader: H2D + voxelize + rulebooks of step i+1
                 pending.clear()                                    # run on a side stream while this step's backward executes
                 pending[(id(src), i + 1)] = net.prepare(mk(i + 1))
             torch.nn.utils.clip_grad_norm_(net.parameters(), 10.0)
@@ -315,9 +332,12 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    if rank == 0:                                  # one nvidia-smi poller per job (rank 0's GPU), at the recipe's 200 ms period: every
-        sampler.start()                            # query takes driver locks that the launching threads of ALL ranks contend for
+    # nvidia-smi needs 0.5-2.5 s to initialise NVML and deliver its first sample, and holds driver-wide locks while it does: started
+    # right before the warm-up (as in round 1) that start-up landed INSIDE the timed steps and stalled one of them by 50-2300 ms
+    # (a single isolated slow step per run, at the same offset from the sampler's start).  It is started early (see above) and the
+    # warm-up only begins once its first sample has arrived.
+    if rank == 0:
+        sampler.wait_first(15.0)
     # Python's cyclic garbage collector is driven by hand, as training loops at scale do (a generation-2 pass over the
     # autograd / rulebook object graph takes 10-30 ms of host time and showed up as isolated 54-78 ms steps): collected
     # between the phases below, never inside a timed step.
@@ -344,6 +364,7 @@ def run_ours(a):
         l0 = _lib.launch_count()
         evs = []
         alloc_trace = []
+        sampler.mark()
         barrier()
         for i in range(a.steps):
             flush.zero_()

@@ -70,6 +70,8 @@ class CPDHotPathDetector(nn.Module):
         self._dense_graph = None
         self.dense_graph_launches = 0           # libcpd_b200 kernels replayed per step by the captured graphs
         self._side = None
+        self._main_mark = None
+        self._pool = None
         self._held = (None, None)
         cfg = model_cfg or MODEL_CFG
         self.pc_range = [float(v) for v in pc_range]
@@ -154,6 +156,15 @@ class CPDHotPathDetector(nn.Module):
         device = next(self.parameters()).device
         if self._side is None:
             self._side = torch.cuda.Stream(device=device, priority=-1)   # high priority: its small kernels must not starve behind the backward
+        # Memory the side stream's pool hands out here may have belonged to the input stage of an earlier step (dropped from
+        # _held), which main-stream kernels of THAT step were still reading when the host let go of it.  Order the side
+        # stream behind the main stream's position at the previous prepare() call (= after the previous step's backward was
+        # enqueued): everything older has then drained, and the step in flight keeps overlapping with this input stage.
+        mark = torch.cuda.Event()
+        mark.record(torch.cuda.current_stream(device))
+        if self._main_mark is not None:
+            self._side.wait_event(self._main_mark)
+        self._main_mark = mark
         with torch.cuda.stream(self._side):
             bd = self._input_stage(batch, device, plan=True)
             ev = torch.cuda.Event()
@@ -161,13 +172,41 @@ class CPDHotPathDetector(nn.Module):
         bd["_ready"] = ev
         return bd
 
+    def prepare_async(self, batch):
+        """prepare() on a worker THREAD: returns a Future whose result() is what prepare() returns.  The input stage's host
+        work (a dozen data-dependent-size syncs on the side stream, ~15 ms of Python enqueue) then runs next to the main
+        thread's forward / backward enqueue instead of after it -- ctypes calls and torch's C++ ops release the GIL.  The
+        stream ordering against the main stream is taken here, on the calling thread; pass the Future to forward()."""
+        import concurrent.futures
+        device = next(self.parameters()).device
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=device, priority=-1)
+        if self._pool is None:
+            self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="cpd-input-stage")
+        mark = torch.cuda.Event()
+        mark.record(torch.cuda.current_stream(device))
+        prev, self._main_mark = self._main_mark, mark
+        grad = torch.is_grad_enabled()
+
+        def work():
+            torch.cuda.set_device(device)                        # the current device is per thread
+            if prev is not None:
+                self._side.wait_event(prev)
+            with torch.cuda.stream(self._side), torch.set_grad_enabled(grad):
+                bd = self._input_stage(batch, device, plan=True)
+                ev = torch.cuda.Event()
+                ev.record(self._side)
+            bd["_ready"] = ev
+            return bd
+        return self._pool.submit(work)
+
     def forward(self, batch, prepared=None):
         """batch: dict(points=[...], points1=[...] (training, MM tower), gt_boxes=(B, M, 8) (training)).
         prepared: the result of prepare(batch) (optional).  Training returns (loss, tb_dict); eval returns
         per-frame prediction dicts."""
         device = next(self.parameters()).device
         if prepared is not None:
-            bd = prepared
+            bd = prepared.result() if hasattr(prepared, "result") else prepared          # prepare_async() hands over a Future
             main = torch.cuda.current_stream(device)
             main.wait_event(bd.pop("_ready"))
             # Tensors made on the side stream return to ITS allocator pool when freed, so they must outlive every kernel
