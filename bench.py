@@ -332,10 +332,9 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # nvidia-smi needs 0.5-2.5 s to initialise NVML and deliver its first sample, and holds driver-wide locks while it does: started
-    # right before the warm-up (as in round 1) that start-up landed INSIDE the timed steps and stalled one of them by 50-2300 ms
-    # (a single isolated slow step per run, at the same offset from the sampler's start).  It is started early (see above) and the
-    # warm-up only begins once its first sample has arrived.
+    # nvidia-smi needs 0.5-2.5 s to initialise NVML and deliver its first sample and takes driver-wide locks while it does: it is
+    # started early (above) and the warm-up only begins once its first sample has arrived, so that start-up cannot land inside a
+    # timed step; its statistics are taken over the timed phases only (sampler.mark()).
     if rank == 0:
         sampler.wait_first(15.0)
     # Python's cyclic garbage collector is driven by hand, as training loops at scale do (a generation-2 pass over the
@@ -346,14 +345,17 @@ def run_ours(a):
     gc.disable()
     with ctx:
         for i in range(a.warmup):
-            run_resident(i)
-        barrier()
+            flush.zero_()
+            res, enc = run_resident(i)             # (kept across the next step exactly as in the timed loop: the previous step's
+        barrier()                                  # outputs -- and the rulebooks they reference -- set the allocator's high-water mark)
         gc.collect()
         if train:
-            # Pre-size the caching allocator: the two batches of the pool differ in size, so the pools of both streams keep
-            # growing by a few tens of MB for ~25 steps (cuMemCreate / cuMemMap under expandable segments), and such a growth
-            # inside a timed step was seen to stall it for 10-280 ms.  Allocating and releasing headroom once leaves it
-            # cached (mapped) in each stream's pool.
+            # Keep the caching allocator from growing inside a timed step.  A device allocation (cuMemCreate / cuMemMap under
+            # expandable segments) drains the queued work and stalled single steps by 10-2300 ms.  Two causes were found: the
+            # timed loop keeps the previous step's outputs (and the rulebooks they reference) alive across the next step while
+            # the warm-up loop did not -- now it does, so the warm-up reaches the same high-water mark -- and the two batches of
+            # the pool differ in size, so both streams' pools keep creeping up by a few tens of MB for ~25 steps: allocating and
+            # releasing headroom once leaves it cached (mapped) in each stream's pool.
             for st in (torch.cuda.current_stream(dev), getattr(net, "_side", None)):
                 if st is not None:
                     with torch.cuda.stream(st):
@@ -404,7 +406,7 @@ def run_ours(a):
         prof_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs_p)
         # ---- end-to-end: host (pinned) inputs in, result scalar out, every step ----
         for i in range(a.warmup):                # the host path has its own first-use costs (staging buffers of the H2D copies in the
-            run_host(i)                          # stream's allocator pool): W untimed steps of it, like the resident leg
+            res, enc = run_host(i)               # stream's allocator pool): W untimed steps of it, like the resident leg
         evs2 = []
         d2h = 0
         gc.collect()
