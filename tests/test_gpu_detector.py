@@ -205,6 +205,16 @@ def test_prepared_input_stage_matches_inline(cuda):
     assert abs(float(loss0) - float(loss1)) <= 1e-4 * max(1.0, abs(float(loss0)))
     loss1.backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in det.parameters())
+    # the same input stage on the worker thread (prepare_async): a Future goes to forward()
+    fut = det.prepare_async(batch)
+    loss2, _ = det(batch, prepared=fut)
+    enc2 = det.last_batch_dict["encoded_spconv_tensor"]
+    assert torch.equal(enc0.indices, enc2.indices)
+    assert abs(float(loss0) - float(loss2)) <= 1e-4 * max(1.0, abs(float(loss0)))
+    futs = [det.prepare_async(batch) for _ in range(3)]          # several in flight, consumed in order
+    for f in futs:
+        l, _ = det(batch, prepared=f)
+        assert abs(float(loss0) - float(l)) <= 1e-4 * max(1.0, abs(float(loss0)))
 
 
 def test_dense_stack_cuda_graph_matches_eager(cuda):

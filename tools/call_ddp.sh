@@ -5,7 +5,7 @@ N=${1:-2}
 mkdir -p gpurun_out
 nproc; nvidia-smi -L | head -8
 echo "== bench N=$N"
-CPD_BENCH_DIAG=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline 2> gpurun_out/bench_n$N.err > gpurun_out/bench_n$N.json
+CPD_BENCH_DIAG=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline ${BENCH_EXTRA:-} 2> gpurun_out/bench_n$N.err > gpurun_out/bench_n$N.json
 tail -3 gpurun_out/bench_n$N.err | cut -c1-300
 python - $N <<'PY'
 import json,sys
