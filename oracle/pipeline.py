@@ -81,6 +81,29 @@ def backbone_forward(net, frames, pc_range, voxel_size, max_pts=5, max_voxels=10
     return feats, coords, shape, stages
 
 
+def backbone_forward_tta(net, stage_frames, pc_range, voxel_size, max_pts=5, max_voxels=1000000):
+    """VoxelBackBone8x's multi-stage eval path (spconv_backbone.py:332-393): stage_frames[i] = list of clouds (one per frame) of
+    TTA stage i.  Stage i's voxels are shifted by i * W along x, ONE tower pass runs on the [D, H, 4 W] grid (neighbouring slabs
+    touch: voxels at a slab border see the next stage's voxels -- reference behaviour, reproduced) and every output is cut back with
+    decompose().  -> list over stages of dict(out=(f, c, shape), x_conv3=..., x_conv4=...)."""
+    w = net.sparse_shape[2]
+    feats, coords = [], []
+    for i, frames in enumerate(stage_frames):
+        for b, pts in enumerate(frames):
+            v, c, n = O.voxelize(pts, pc_range, voxel_size, max_pts, max_voxels)
+            feats.append(O.mean_vfe(v, n))
+            cc = np.concatenate([np.full((len(c), 1), b, np.int32), c], 1)
+            cc[:, 3] += i * w
+            coords.append(cc)
+    feats, coords = np.concatenate(feats, 0), np.concatenate(coords, 0)
+    shape, cache, stages = [net.sparse_shape[0], net.sparse_shape[1], 4 * w], {}, {}
+    for name in ["conv_input", "conv1", "conv2", "conv3", "conv4", "conv_out"]:
+        feats, coords, shape = run_sequential(getattr(net, name), feats, coords, shape, cache)
+        stages[name] = (feats, coords, list(shape))
+    return [dict(out=decompose(*stages["conv_out"], i), x_conv3=decompose(*stages["conv3"], i), x_conv4=decompose(*stages["conv4"], i))
+            for i in range(len(stage_frames))]
+
+
 def bev_dense(feats, coords, batch, shape):
     d = O.dense(feats, coords, batch, shape)
     n, c, dd, h, w = d.shape

@@ -280,3 +280,28 @@ def test_table_permute_and_transpose_match_torch(cuda, m, K):
     assert torch.equal(masks, ops.tile_tap_masks(ref))
     t = ops.table_transpose(nbr)
     assert t.shape == (K, m) and torch.equal(t, nbr.t().contiguous())
+
+
+def test_multi_stage_tta_eval_at_full_width(cuda, oracle):
+    """VoxelBackBone8x eval with 3 TTA stages on the real grid: one tower pass over [41, 1504, 6016] (X-concatenated stages),
+    strict-`<` decompose per stage (spconv_backbone.py:241-260,332-393) == the oracle pipeline on the same concatenated input."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_tta_cpu import check_tta
+    from cpd_b200 import backbone, voxel
+    torch.manual_seed(0)
+    net = backbone.VoxelBackBone8x(dict(NUM_FILTERS=[16, 32, 64, 128], OUT_FEATURES=128), 5, [1504, 1504, 40])
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.uniform_(-0.2, 0.2); m.running_var.uniform_(0.5, 1.5); m.weight.data.uniform_(0.7, 1.3); m.bias.data.uniform_(-0.2, 0.2)
+    net = net.to(cuda).eval()
+    stage_frames = [[synth_scan(12000, 30 + i)] for i in range(3)]
+    bd = dict(batch_size=1, transform_param=torch.zeros(1, 3, 3, device=cuda))
+    for i, frames in enumerate(stage_frames):
+        sid = "" if i == 0 else str(i)
+        v = voxel.voxelize_batch([torch.from_numpy(f).to(cuda) for f in frames], PC_RANGE, VOXEL_SIZE)
+        bd["voxel_features" + sid], bd["voxel_coords" + sid] = v["voxel_features"], v["voxel_coords"]
+    with torch.no_grad():
+        out = net(bd)
+    check_tta(net, out, stage_frames, PC_RANGE, VOXEL_SIZE)
