@@ -212,8 +212,9 @@ class CPDHotPathDetector(nn.Module):
             # Tensors made on the side stream return to ITS allocator pool when freed, so they must outlive every kernel
             # of this step on the main stream.  Rather than record_stream() on hundreds of tensors (which parks their
             # blocks behind events and makes the side pool grow through cudaMalloc), the previous step's input stage is
-            # simply kept alive until this forward has been enqueued; the host sync at the end of forward (NMS count)
-            # then guarantees the step that used it has drained before its memory can be handed out again.
+            # simply kept alive until this forward has been enqueued; prepare() / prepare_async() order the side stream
+            # behind the main stream's previous-step mark, so whatever is released here is no longer being read when the side
+            # stream's next kernels can touch it.
             self._held = (self._held[1], dict(bd))
         else:
             bd = self._input_stage(batch, device, plan=False)
