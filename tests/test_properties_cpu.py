@@ -124,3 +124,35 @@ def test_dense_round_trip(oracle, seed, m, c, batch):
         back = d[coords[:, 0], :, coords[:, 1], coords[:, 2], coords[:, 3]]
         assert np.array_equal(back, feat)                                    # gather(dense(x)) == x
     assert np.count_nonzero(d) == np.count_nonzero(feat)                     # nothing else is written
+
+
+def _boxes(seed, n):
+    g = np.random.default_rng(seed)
+    c = g.uniform(-8, 8, (max(n // 4, 1), 2))
+    xy = c[g.integers(0, len(c), n)] + g.normal(0, 0.7, (n, 2))
+    return np.concatenate([xy, g.uniform(-1, 1, (n, 1)), g.uniform(0.6, 5.0, (n, 2)), g.uniform(1.0, 2.0, (n, 1)), g.uniform(-3.2, 3.2, (n, 1))],
+                          1).astype(np.float32)
+
+
+@settings(**FAST)
+@given(seed=st.integers(0, 10 ** 6), n=st.integers(1, 120), thresh=st.sampled_from([0.1, 0.5, 0.8]))
+def test_rotated_iou_and_nms_invariants(oracle, seed, n, thresh):
+    b = _boxes(seed, n)
+    iou = oracle.iou_bev(b, b)
+    assert iou.shape == (n, n) and np.all(iou >= 0) and np.all(iou <= 1 + 1e-4)
+    assert np.allclose(np.diag(iou), 1.0, atol=2e-3)                          # a box overlaps itself completely (fp32 clipping slack)
+    assert np.allclose(iou, iou.T, atol=2e-3)                                 # symmetric up to the clipping order
+    far = b.copy()
+    far[:, 0] += 100.0
+    assert not oracle.iou_bev(b, far).any()                                   # disjoint boxes
+    keep = oracle.nms(b, thresh)                                              # boxes are taken as already score-sorted
+    assert keep[0] == 0 and np.all(np.diff(keep) > 0)                         # the best box always survives; order is kept
+    kept = b[keep]
+    sub = np.triu(oracle.iou_bev(kept, kept), 1)
+    assert sub.max(initial=0.0) <= thresh + 1e-5                              # survivors do not overlap above the threshold
+    removed = np.setdiff1d(np.arange(n), keep)
+    if len(removed):                                                          # every removed box is covered by an earlier survivor
+        cover = oracle.iou_bev(b[removed], kept)
+        earlier = np.asarray(keep)[None, :] < removed[:, None]
+        assert np.all((cover * earlier).max(1) > thresh)
+    assert np.array_equal(oracle.nms(kept, thresh), np.arange(len(kept)))     # idempotent
