@@ -156,3 +156,57 @@ def test_rotated_iou_and_nms_invariants(oracle, seed, n, thresh):
         earlier = np.asarray(keep)[None, :] < removed[:, None]
         assert np.all((cover * earlier).max(1) > thresh)
     assert np.array_equal(oracle.nms(kept, thresh), np.arange(len(kept)))     # idempotent
+
+
+@settings(max_examples=20, deadline=None, suppress_health_check=list(HealthCheck))
+@given(seed=st.integers(0, 10 ** 6), dims=st.tuples(st.integers(3, 9), st.integers(4, 13), st.integers(4, 11)),
+       geom=st.sampled_from([((3, 3, 3), (1, 1, 1), (1, 1, 1)), ((3, 3, 3), (2, 2, 2), (1, 1, 1)), ((3, 3, 3), (2, 2, 2), (0, 1, 1)),
+                             ((3, 1, 1), (2, 1, 1), (0, 0, 0)), ((3, 3, 3), (1, 2, 2), (1, 1, 1)), ((1, 3, 3), (1, 1, 1), (0, 1, 1))]),
+       cin=st.integers(1, 6), cout=st.integers(1, 5), fill=st.floats(0.05, 0.6))
+def test_sparse_conv_equals_dense_conv3d_on_random_geometry(oracle, seed, dims, geom, cin, cout, fill):
+    """The independent pin of the spconv restatement (tests/test_oracle_cpu.py) over random grids, kernel / stride / padding
+    combinations, channel counts and occupancies: forward and all three gradients == torch conv3d on the densified input,
+    read at the active outputs; the active output set == the cells with a non-empty receptive field."""
+    import torch
+    ks, stv, pd = geom
+    subm = stv == (1, 1, 1) and all(k % 2 == 1 for k in ks) and pd == tuple(k // 2 for k in ks)
+    shape, batch = list(dims), 2
+    g = np.random.default_rng(seed)
+    ncell = batch * shape[0] * shape[1] * shape[2]
+    cells = np.sort(g.choice(ncell, size=max(1, int(fill * ncell)), replace=False))
+    b, r = np.divmod(cells, shape[0] * shape[1] * shape[2])
+    z, r = np.divmod(r, shape[1] * shape[2])
+    y, x = np.divmod(r, shape[2])
+    coords = np.stack([b, z, y, x], 1).astype(np.int32)
+    xf = g.normal(0, 1, (len(coords), cin)).astype(np.float32)
+    w = g.normal(0, 0.4, (cout, *ks, cin)).astype(np.float32)
+    bias = g.normal(0, 0.2, cout).astype(np.float32)
+    osh = [(shape[i] + 2 * pd[i] - ks[i]) // stv[i] + 1 for i in range(3)]
+    if min(osh) <= 0:
+        return
+    rb = oracle.rulebook_subm(coords, shape, list(ks)) if subm else oracle.rulebook_strided(coords, shape, list(ks), list(stv), list(pd))
+    yv = oracle.spconv_fwd(xf, w, bias, rb)
+    xd = torch.zeros(batch, cin, *shape, dtype=torch.float64)
+    xd[coords[:, 0], :, coords[:, 1], coords[:, 2], coords[:, 3]] = torch.from_numpy(xf).double()
+    xd.requires_grad_(True)
+    wt = torch.from_numpy(w).double().permute(0, 4, 1, 2, 3).contiguous().requires_grad_(True)
+    bt = torch.from_numpy(bias).double().requires_grad_(True)
+    yd = torch.nn.functional.conv3d(xd, wt, bt, stride=list(stv), padding=list(pd))
+    oc = rb.out_coords
+    assert list(yd.shape[2:]) == list(rb.out_shape)
+    if not subm:
+        occ_in = torch.zeros(batch, 1, *shape, dtype=torch.float64)
+        occ_in[coords[:, 0], 0, coords[:, 1], coords[:, 2], coords[:, 3]] = 1.0
+        occ = torch.nn.functional.conv3d(occ_in, torch.ones(1, 1, *ks, dtype=torch.float64), stride=list(stv), padding=list(pd))
+        assert int((occ > 0).sum()) == rb.m_out
+    got = yd[oc[:, 0], :, oc[:, 1], oc[:, 2], oc[:, 3]]
+    scale = max(1.0, float(got.detach().abs().max()))
+    assert float(np.abs(got.detach().numpy() - yv).max()) <= 1e-4 * scale
+    dy = g.normal(0, 1, yv.shape).astype(np.float32)
+    dx, dw, db = oracle.spconv_bwd(xf, w, dy, rb)
+    (got * torch.from_numpy(dy).double()).sum().backward()
+    gx = xd.grad[coords[:, 0], :, coords[:, 1], coords[:, 2], coords[:, 3]].numpy()
+    assert float(np.abs(gx - dx).max()) <= 1e-4 * max(1.0, float(np.abs(gx).max()))
+    gw = wt.grad.permute(0, 2, 3, 4, 1).numpy()
+    assert float(np.abs(gw - dw).max()) <= 1e-4 * max(1.0, float(np.abs(gw).max()))
+    assert float(np.abs(bt.grad.numpy() - db).max()) <= 1e-4 * max(1.0, float(np.abs(db).max()))
